@@ -1,0 +1,267 @@
+"""ek-pnp-3d_b200 -- B200-native coupled electrokinetic time step (host mirror).
+
+Thin ctypes layer over ``libek_b200.so`` (include/ek_b200.h).  The Python
+names mirror the reference's host functions for the hot path
+(``initialization``, ``init_equilibrium``, ``stream_collide_save``,
+``fast_Poisson``; LBM.h:159-176 of gyf135/EK-PNP-3D) so that tests read like
+the reference's ``main()``.
+
+There is no CPU path: importing works anywhere (the library only needs the
+CUDA runtime to load), but creating a simulation without the built library or
+without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libek_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "ek_b200.h")
+
+FIELDS = ("rho", "ux", "uy", "uz", "charge", "chargen", "phi", "T", "Ex", "Ey", "Ez")
+SETS = ("fluid", "cation", "anion", "temperature")
+STREAM_AA, STREAM_PUSH = 0, 1
+
+_STATUS = {0: "EK_OK", 1: "EK_ERR_INVALID", 2: "EK_ERR_CUDA", 3: "EK_ERR_CUFFT", 4: "EK_ERR_STATE", 5: "EK_ERR_NOMEM"}
+
+
+class EkError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    """ek_params of include/ek_b200.h (the constants of LBM.h:29-125)."""
+    _fields_ = [
+        ("NX", C.c_int), ("NY", C.c_int), ("NZ", C.c_int),
+        ("Lx", C.c_double), ("Ly", C.c_double), ("Lz", C.c_double),
+        ("dx", C.c_double), ("dy", C.c_double), ("dz", C.c_double),
+        ("uw", C.c_double), ("exf", C.c_double),
+        ("CFL", C.c_double), ("dt", C.c_double), ("cs_square", C.c_double), ("rho0", C.c_double),
+        ("chargeinf", C.c_double),
+        ("voltage", C.c_double), ("voltage2", C.c_double),
+        ("Ext", C.c_double), ("eps", C.c_double),
+        ("diffu", C.c_double), ("nu", C.c_double), ("K", C.c_double),
+        ("diffun", C.c_double), ("Kn", C.c_double),
+        ("kB", C.c_double), ("electron", C.c_double), ("roomT", C.c_double),
+        ("convertCtoCharge", C.c_double), ("PB_omega", C.c_double),
+        ("D", C.c_double), ("Ra", C.c_double), ("TH", C.c_double),
+        ("w0", C.c_double), ("ws", C.c_double), ("wa", C.c_double), ("wd", C.c_double),
+        ("V", C.c_double), ("VC", C.c_double), ("VCn", C.c_double), ("VT", C.c_double),
+        ("pb_iters", C.c_int),
+    ]
+
+    def as_dict(self) -> dict:
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+_lib = None
+
+
+def load_library():
+    """Load libek_b200.so; fail loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EkError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C ek-pnp-3d_b200/csrc`. There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    H = C.c_void_p
+    L.ek_abi_version.restype = C.c_int
+    L.ek_default_params.argtypes = [C.POINTER(Params)]
+    L.ek_default_params.restype = None
+    L.ek_create.argtypes = [C.POINTER(Params), C.c_int, C.POINTER(H)]
+    for name in ("ek_destroy", "ek_init_fields", "ek_init_equilibrium", "ek_init", "ek_sync", "ek_reset_counters"):
+        getattr(L, name).argtypes = [H]
+    L.ek_set_fields.argtypes = [H, C.POINTER(C.c_void_p), C.c_int]
+    L.ek_step.argtypes = [H, C.c_int]
+    L.ek_stream_collide_save.argtypes = [H, C.c_int]
+    L.ek_fast_poisson.argtypes = [H, C.c_int]
+    L.ek_get_field.argtypes = [H, C.c_int, C.c_void_p, C.c_int]
+    L.ek_field_ptr.argtypes = [H, C.c_int, C.POINTER(C.c_void_p)]
+    L.ek_get_populations.argtypes = [H, C.c_int, C.c_void_p, C.c_int]
+    L.ek_set_option.argtypes = [H, C.c_char_p, C.c_longlong]
+    L.ek_get_counter.argtypes = [H, C.c_char_p, C.POINTER(C.c_double)]
+    L.ek_stream.argtypes = [H]
+    L.ek_stream.restype = C.c_void_p
+    L.ek_last_error.argtypes = [H]
+    L.ek_last_error.restype = C.c_char_p
+    L.ek_wall_current.argtypes = [H, C.POINTER(C.c_double)]
+    L.ek_max_uz.argtypes = [H, C.POINTER(C.c_double)]
+    L.ek_save_data_tecplot.argtypes = [H, C.c_char_p, C.c_double, C.c_int, C.c_int]
+    L.ek_save_data_end.argtypes = [H, C.c_char_p, C.c_double]
+    _lib = L
+    return L
+
+
+def default_params(**over) -> Params:
+    """LBM.h as shipped with overrides; Lx, Ly, Lz follow the grid unless given."""
+    p = Params()
+    load_library().ek_default_params(C.byref(p))
+    for k, v in over.items():
+        if not hasattr(p, k):
+            raise KeyError(k)
+        setattr(p, k, v)
+    if "Lx" not in over:
+        p.Lx = p.NX * p.dx
+    if "Ly" not in over:
+        p.Ly = p.NY * p.dy
+    if "Lz" not in over:
+        p.Lz = (p.NZ - 1) * p.dz
+    return p
+
+
+class Simulation:
+    """One coupled EK-PNP simulation on one CUDA device."""
+
+    def __init__(self, params: Params | None = None, device: int = -1, stream_mode: int | None = None,
+                 zchunk: int | None = None, profile: bool = False):
+        self.L = load_library()
+        self.p = params if params is not None else default_params()
+        self.h = C.c_void_p()
+        st = self.L.ek_create(C.byref(self.p), int(device), C.byref(self.h))
+        if st != 0:
+            self.h = C.c_void_p()
+            raise EkError(f"ek_create failed: {_STATUS.get(st, st)} (is a CUDA device present? there is no CPU path)")
+        self.shape = (self.p.NZ, self.p.NY, self.p.NX)
+        self.ncells = self.p.NX * self.p.NY * self.p.NZ
+        self.t = 0.0
+        if stream_mode is not None:
+            self.set_option("stream_mode", stream_mode)
+        if zchunk is not None:
+            self.set_option("zchunk", zchunk)
+        if profile:
+            self.set_option("profile", 1)
+
+    # -- plumbing ---------------------------------------------------------
+    def _ck(self, st: int, what: str):
+        if st != 0:
+            msg = self.L.ek_last_error(self.h)
+            raise EkError(f"{what}: {_STATUS.get(st, st)}: {msg.decode() if msg else ''}")
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.L.ek_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_option(self, key: str, value: int):
+        self._ck(self.L.ek_set_option(self.h, key.encode(), int(value)), f"ek_set_option({key})")
+
+    def counter(self, key: str) -> float:
+        v = C.c_double()
+        self._ck(self.L.ek_get_counter(self.h, key.encode(), C.byref(v)), f"ek_get_counter({key})")
+        return v.value
+
+    def reset_counters(self):
+        self._ck(self.L.ek_reset_counters(self.h), "ek_reset_counters")
+
+    def sync(self):
+        self._ck(self.L.ek_sync(self.h), "ek_sync")
+
+    @property
+    def stream(self) -> int:
+        return self.L.ek_stream(self.h) or 0
+
+    # -- the reference's call sequence --------------------------------------
+    def initialization(self):
+        """initialization() of the reference (LBM.cu:68-146)."""
+        self._ck(self.L.ek_init_fields(self.h), "ek_init_fields")
+        self.t = 0.0
+
+    def init_equilibrium(self):
+        """init_equilibrium() of the reference (LBM.cu:150-463)."""
+        self._ck(self.L.ek_init_equilibrium(self.h), "ek_init_equilibrium")
+
+    def init(self):
+        self.initialization()
+        self.init_equilibrium()
+
+    def stream_collide_save(self, write_fields: bool = True):
+        """stream_collide_save() of the reference (LBM.cu:465-481)."""
+        self._ck(self.L.ek_stream_collide_save(self.h, int(write_fields)), "ek_stream_collide_save")
+
+    def fast_Poisson(self, write_efield: bool = True):
+        """fast_Poisson() of the reference (poisson.cu:75-103)."""
+        self._ck(self.L.ek_fast_poisson(self.h, int(write_efield)), "ek_fast_poisson")
+
+    def step(self, nsteps: int = 1):
+        """nsteps iterations of the loop body main.cu:189-200."""
+        self._ck(self.L.ek_step(self.h, int(nsteps)), "ek_step")
+        self.t += nsteps * self.p.dt
+
+    # -- data ---------------------------------------------------------------
+    def set_fields(self, fields: dict):
+        """Upload macroscopic arrays (any subset of FIELDS), shape (NZ,NY,NX)."""
+        arr = (C.c_void_p * len(FIELDS))()
+        keep = []
+        for i, n in enumerate(FIELDS):
+            if n in fields and fields[n] is not None:
+                a = np.ascontiguousarray(fields[n], dtype=np.float64)
+                if a.size != self.ncells:
+                    raise ValueError(f"field {n}: expected {self.ncells} values, got {a.size}")
+                keep.append(a)
+                arr[i] = a.ctypes.data
+            else:
+                arr[i] = None
+        self._ck(self.L.ek_set_fields(self.h, arr, 0), "ek_set_fields")
+
+    def set_fields_device(self, ptrs: dict):
+        """Same with device pointers (ints), e.g. torch tensors' data_ptr()."""
+        arr = (C.c_void_p * len(FIELDS))()
+        for i, n in enumerate(FIELDS):
+            arr[i] = ptrs.get(n)
+        self._ck(self.L.ek_set_fields(self.h, arr, 1), "ek_set_fields")
+
+    def field(self, name: str, out: np.ndarray | None = None) -> np.ndarray:
+        a = out if out is not None else np.empty(self.shape, dtype=np.float64)
+        self._ck(self.L.ek_get_field(self.h, FIELDS.index(name), a.ctypes.data, 0), f"ek_get_field({name})")
+        return a
+
+    def field_to_device(self, name: str, dev_ptr: int):
+        self._ck(self.L.ek_get_field(self.h, FIELDS.index(name), C.c_void_p(dev_ptr), 1), f"ek_get_field({name})")
+
+    def fields(self) -> dict:
+        return {n: self.field(n) for n in FIELDS}
+
+    def populations(self, s: int | str) -> np.ndarray:
+        """Pre-collision populations, shape (27, NZ, NY, NX), reference layout."""
+        if isinstance(s, str):
+            s = SETS.index(s)
+        a = np.empty((27,) + self.shape, dtype=np.float64)
+        self._ck(self.L.ek_get_populations(self.h, int(s), a.ctypes.data, 0), "ek_get_populations")
+        return a
+
+    # -- diagnostics and dumps (LBM.cu:2492-2753) -----------------------------
+    def current(self) -> float:
+        v = C.c_double()
+        self._ck(self.L.ek_wall_current(self.h, C.byref(v)), "ek_wall_current")
+        return v.value
+
+    def max_uz(self) -> float:
+        v = C.c_double()
+        self._ck(self.L.ek_max_uz(self.h, C.byref(v)), "ek_max_uz")
+        return v.value
+
+    def save_data_tecplot(self, path: str, time: float | None = None, append: bool = False, first: bool = True):
+        self._ck(self.L.ek_save_data_tecplot(self.h, path.encode(), self.t if time is None else time,
+                                             int(append), int(first)), "ek_save_data_tecplot")
+
+    def save_data_end(self, path: str, time: float | None = None):
+        self._ck(self.L.ek_save_data_end(self.h, path.encode(), self.t if time is None else time),
+                 "ek_save_data_end")

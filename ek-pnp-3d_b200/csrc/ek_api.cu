@@ -1,0 +1,452 @@
+// ek_api.cu -- the C ABI of include/ek_b200.h: handle life cycle, start-up,
+// the coupled step loop (main.cu:189-200 of the reference) and accessors.
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "ek_handle.h"
+
+void ek_set_error(ek_handle *h, const std::string &msg)
+{
+    if (h) h->err = msg;
+}
+
+namespace {
+
+__global__ void k_dq_from_fields(EkConst c, const double *ch, const double *chn, double *dq)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= c.NX) return;
+    const size_t i = (size_t)blockIdx.z * c.plane + blockIdx.y * c.PX + x;
+    dq[i] = ch[i] - chn[i];
+}
+
+// derived constants, each evaluated in the form the reference uses
+void compute_consts(const ek_params &p, EkConst &c)
+{
+    memset(&c, 0, sizeof(c));
+    c.NX = p.NX; c.NY = p.NY; c.NZ = p.NZ;
+    c.PX = p.NX;
+    c.xlo = p.NX - 1;
+    c.xhi = 0;
+    c.plane = (long long)c.NY * c.PX;
+    c.N = (long long)c.NZ * c.plane;
+    const double dt = p.dt, cs2 = p.cs_square;
+    c.cflinv = 1.0 / p.CFL;
+    c.cflinv2 = c.cflinv * c.cflinv / cs2;
+    c.inv_cs2 = 1.0 / cs2;
+    c.cs_square = cs2;
+    c.CFL = p.CFL;
+    c.tfac = 1.0 / cs2 / p.CFL;
+    c.dt = dt;
+    c.CtoC = p.convertCtoCharge; c.Ext = p.Ext; c.exf = p.exf; c.eps = p.eps;
+    c.rho0 = p.rho0; c.Ra = p.Ra; c.nu = p.nu; c.D = p.D;
+    c.K = p.K; c.Kn = p.Kn;
+    c.w[0] = p.w0; c.w[1] = p.ws; c.w[2] = p.wa; c.w[3] = p.wd;
+    for (int k = 0; k < 4; ++k) c.coe[k] = c.w[k] / cs2;
+    // LBM.cu:488-495
+    const double omega_plus = 1.0 / (p.nu / cs2 / dt + 1.0 / 2.0) / dt;
+    const double omega_minus = 1.0 / (p.V / (p.nu / cs2 / dt) + 1.0 / 2.0) / dt;
+    const double omega_c_minus = 1.0 / (p.diffu / cs2 / dt + 1.0 / 2.0) / dt;
+    const double omega_c_plus = 1.0 / (p.VC / (p.diffu / cs2 / dt) + 1.0 / 2.0) / dt;
+    const double omega_cn_minus = 1.0 / (p.diffun / cs2 / dt + 1.0 / 2.0) / dt;
+    const double omega_cn_plus = 1.0 / (p.VCn / (p.diffun / cs2 / dt) + 1.0 / 2.0) / dt;
+    const double omega_T_minus = 1.0 / (p.D / cs2 / dt + 1.0 / 2.0) / dt;
+    const double omega_T_plus = 1.0 / (p.VT / (p.D / cs2 / dt) + 1.0 / 2.0) / dt;
+    // LBM.cu:1700-1707
+    c.wp[0] = omega_plus * dt;    c.wm[0] = omega_minus * dt;
+    c.wp[1] = omega_c_plus * dt;  c.wm[1] = omega_c_minus * dt;
+    c.wp[2] = omega_cn_plus * dt; c.wm[2] = omega_cn_minus * dt;
+    c.wp[3] = omega_T_plus * dt;  c.wm[3] = omega_T_minus * dt;
+    // LBM.cu:1660-1661
+    c.sp = 1.0 - 0.5 * dt * omega_plus;
+    c.sm = 1.0 - 0.5 * dt * omega_minus;
+    // LBM.cu:1896-1898
+    c.multi[0] = 0.0;
+    c.multi[1] = 2.0 * p.rho0 * p.uw / cs2 * p.ws / p.CFL;
+    c.multi[2] = 2.0 * p.rho0 * p.uw / cs2 * p.wa / p.CFL;
+    c.multi[3] = 2.0 * p.rho0 * p.uw / cs2 * p.wd / p.CFL;
+    // LBM.cu:2226-2229
+    for (int k = 0; k < 4; ++k) c.twoTw[k] = 2.0 * p.TH * c.w[k];
+    c.dx = p.dx; c.dy = p.dy; c.dz = p.dz;
+    c.voltage = p.voltage; c.voltage2 = p.voltage2;
+}
+
+void free_state(ek_handle *h)
+{
+    for (int l = 0; l < 2; ++l)
+        for (int s = 0; s < 4; ++s) { cudaFree(h->lat[l][s]); h->lat[l][s] = nullptr; }
+    cudaFree(h->wall); h->wall = nullptr;
+    for (int k = 0; k < EK_NFIELDS; ++k) { cudaFree(h->fld[k]); h->fld[k] = nullptr; }
+    cudaFree(h->dq); h->dq = nullptr;
+    cudaFree(h->phi_old); h->phi_old = nullptr;
+    ek_poisson_destroy(h->poisson);
+    h->allocated = false;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (dev != prev) cudaSetDevice(dev); }
+    ~DeviceGuard() { int cur; cudaGetDevice(&cur); if (cur != prev && prev >= 0) cudaSetDevice(prev); }
+};
+
+void collect_events(ek_handle *h)
+{
+    for (auto &e : h->ev_lbm) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e.first, e.second);
+        h->lbm_ms += ms;
+        cudaEventDestroy(e.first); cudaEventDestroy(e.second);
+    }
+    h->ev_lbm.clear();
+    for (auto &e : h->ev_poi) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e.first, e.second);
+        h->poisson_ms += ms;
+        cudaEventDestroy(e.first); cudaEventDestroy(e.second);
+    }
+    h->ev_poi.clear();
+}
+
+}  // namespace
+
+ek_status ek_alloc_state(ek_handle *h)
+{
+    if (h->allocated) return EK_OK;
+    const size_t N = (size_t)h->c.N;
+    const int nlat = h->stream_mode == EK_STREAM_PUSH ? 2 : 1;
+    for (int l = 0; l < nlat; ++l)
+        for (int s = 0; s < 4; ++s) EK_CUDA(h, cudaMalloc((void **)&h->lat[l][s], 27 * N * sizeof(double)));
+    EK_CUDA(h, cudaMalloc((void **)&h->wall, (size_t)3 * 2 * 27 * h->c.plane * sizeof(double)));
+    for (int k = 0; k < EK_NFIELDS; ++k) {
+        EK_CUDA(h, cudaMalloc((void **)&h->fld[k], N * sizeof(double)));
+        EK_CUDA(h, cudaMemsetAsync(h->fld[k], 0, N * sizeof(double), h->stream));
+    }
+    EK_CUDA(h, cudaMalloc((void **)&h->dq, N * sizeof(double)));
+    EK_CUDA(h, cudaMalloc((void **)&h->phi_old, N * sizeof(double)));
+    ek_status st = ek_poisson_create(h, h->poisson, h->p, h->c.PX, h->stream);
+    if (st != EK_OK) return st;
+    h->allocated = true;
+    return EK_OK;
+}
+
+StepArgs ek_step_args(ek_handle *h)
+{
+    StepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.c = h->c;
+    const bool push = h->stream_mode == EK_STREAM_PUSH;
+    for (int s = 0; s < 4; ++s) {
+        a.in[s] = h->lat[push ? h->cur : 0][s];
+        a.out[s] = h->lat[push ? (h->cur ^ 1) : 0][s];
+    }
+    a.wall = h->wall;
+    a.phi = h->fld[EK_PHI];
+    a.E[0] = h->fld[EK_EX]; a.E[1] = h->fld[EK_EY]; a.E[2] = h->fld[EK_EZ];
+    a.dq = h->dq;
+    a.fld[0] = h->fld[EK_RHO]; a.fld[1] = h->fld[EK_UX]; a.fld[2] = h->fld[EK_UY]; a.fld[3] = h->fld[EK_UZ];
+    a.fld[4] = h->fld[EK_CHARGE]; a.fld[5] = h->fld[EK_CHARGEN]; a.fld[6] = h->fld[EK_T];
+    a.zchunk = h->zchunk;
+    return a;
+}
+
+extern "C" {
+
+int ek_abi_version(void) { return EK_B200_ABI_VERSION; }
+
+void ek_default_params(ek_params *p)
+{
+    // LBM.h:29-125 as shipped
+    p->NX = 50; p->NY = 8; p->NZ = 51;
+    p->Lx = 0.5e-6; p->Ly = 0.08e-6; p->Lz = 0.5e-6;
+    p->dx = 1.0e-6 / 100.0; p->dy = 1.0e-6 / 100.0; p->dz = 1.0e-6 / 100.0;
+    p->uw = 0.0; p->exf = 0.0;
+    p->CFL = 0.01;
+    p->dt = 0.01 * 1.0e-6 / 100.0;
+    p->cs_square = 1.0 / 3.0 / (0.01 * 0.01);
+    p->rho0 = 1000.0;
+    p->chargeinf = 0.01;
+    p->voltage = -5.2574e-3; p->voltage2 = -5.2574e-3;
+    p->Ext = 1.0e4; p->eps = 6.95e-10;
+    p->diffu = 1.0e-8; p->nu = 0.889e-6; p->K = 4.245e-7;
+    p->diffun = 1.0e-8; p->Kn = -4.245e-7;
+    p->kB = 1.38e-23; p->electron = 1.6e-19; p->roomT = 273.0;
+    p->convertCtoCharge = 9.64e4; p->PB_omega = 0.05;
+    p->D = 0.889e-6; p->Ra = 1; p->TH = 1;
+    p->w0 = 8.0 / 27.0; p->ws = 2.0 / 27.0; p->wa = 1.0 / 54.0; p->wd = 1.0 / 216.0;
+    p->V = 1.0 / 12.0; p->VC = 1.0e-6; p->VCn = 1.0e-6; p->VT = 1.0 / 12.0;
+    p->pb_iters = 501;
+}
+
+ek_status ek_create(const ek_params *p, int device, ek_handle **out)
+{
+    if (!p || !out) return EK_ERR_INVALID;
+    *out = nullptr;
+    if (p->NX < 2 || p->NY < 1 || p->NZ < 5) return EK_ERR_INVALID;
+    if (p->NY > 65535 || p->NZ > 65535) return EK_ERR_INVALID;
+    if ((long long)p->NX * p->NY * p->NZ >= (1LL << 31)) return EK_ERR_INVALID;  // per-slot index is 32-bit
+    if (!(p->dt > 0) || !(p->CFL > 0) || !(p->cs_square > 0) || !(p->dz > 0)) return EK_ERR_INVALID;
+    ek_handle *h = new (std::nothrow) ek_handle();
+    if (!h) return EK_ERR_NOMEM;
+    h->p = *p;
+    compute_consts(*p, h->c);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        // no silent CPU path: the product requires a CUDA device
+        delete h;
+        return EK_ERR_CUDA;
+    }
+    if (device < 0) cudaGetDevice(&h->device); else h->device = device;
+    if (h->device >= ndev) { delete h; return EK_ERR_INVALID; }
+    DeviceGuard g(h->device);
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return EK_ERR_CUDA; }
+    *out = h;
+    return EK_OK;
+}
+
+ek_status ek_destroy(ek_handle *h)
+{
+    if (!h) return EK_OK;
+    DeviceGuard g(h->device);
+    cudaStreamSynchronize(h->stream);
+    collect_events(h);
+    free_state(h);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return EK_OK;
+}
+
+const char *ek_last_error(ek_handle *h) { return h ? h->err.c_str() : "null handle"; }
+void *ek_stream(ek_handle *h) { return h ? (void *)h->stream : nullptr; }
+
+ek_status ek_set_option(ek_handle *h, const char *key, long long value)
+{
+    if (!h || !key) return EK_ERR_INVALID;
+    if (!strcmp(key, "stream_mode")) {
+        if (h->allocated) { ek_set_error(h, "stream_mode must be set before the first init/set_fields"); return EK_ERR_STATE; }
+        if (value != EK_STREAM_AA && value != EK_STREAM_PUSH) return EK_ERR_INVALID;
+        h->stream_mode = (int)value;
+        return EK_OK;
+    }
+    if (!strcmp(key, "zchunk")) {
+        if (value < 2) return EK_ERR_INVALID;  // the owner of z = 0 must own z = 1
+        h->zchunk = (int)value;
+        return EK_OK;
+    }
+    if (!strcmp(key, "profile")) { h->profile = value != 0; return EK_OK; }
+    return EK_ERR_INVALID;
+}
+
+ek_status ek_sync(ek_handle *h)
+{
+    if (!h) return EK_ERR_INVALID;
+    DeviceGuard g(h->device);
+    EK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return EK_OK;
+}
+
+ek_status ek_get_counter(ek_handle *h, const char *key, double *value)
+{
+    if (!h || !key || !value) return EK_ERR_INVALID;
+    DeviceGuard g(h->device);
+    if (!strcmp(key, "steps")) { *value = (double)h->steps; return EK_OK; }
+    if (!strcmp(key, "lbm_launches")) { *value = (double)h->lbm_launches; return EK_OK; }
+    if (!strcmp(key, "poisson_launches")) { *value = (double)h->poisson_launches; return EK_OK; }
+    if (!strcmp(key, "kernel_launches")) { *value = (double)(h->lbm_launches + h->poisson_launches); return EK_OK; }
+    if (!strcmp(key, "lbm_ms") || !strcmp(key, "poisson_ms")) {
+        EK_CUDA(h, cudaStreamSynchronize(h->stream));
+        collect_events(h);
+        *value = !strcmp(key, "lbm_ms") ? h->lbm_ms : h->poisson_ms;
+        return EK_OK;
+    }
+    return EK_ERR_INVALID;
+}
+
+ek_status ek_reset_counters(ek_handle *h)
+{
+    if (!h) return EK_ERR_INVALID;
+    DeviceGuard g(h->device);
+    EK_CUDA(h, cudaStreamSynchronize(h->stream));
+    collect_events(h);
+    h->steps = h->lbm_launches = h->poisson_launches = 0;
+    h->lbm_ms = h->poisson_ms = 0.0;
+    return EK_OK;
+}
+
+ek_status ek_init_fields(ek_handle *h)
+{
+    if (!h) return EK_ERR_INVALID;
+    DeviceGuard g(h->device);
+    ek_status st = ek_alloc_state(h);
+    if (st != EK_OK) return st;
+    const EkConst &c = h->c;
+    const size_t bytes = (size_t)c.N * sizeof(double);
+    ek_launch_initialization(c, h->p, h->fld, h->stream);                       // LBM.cu:76
+    EK_CUDA(h, cudaMemcpyAsync(h->phi_old, h->fld[EK_PHI], bytes, cudaMemcpyDeviceToDevice, h->stream));  // LBM.cu:82-86
+    for (int i = 0; i < h->p.pb_iters; ++i) {                                     // LBM.cu:89
+        ek_launch_pbe(c, h->p, h->fld[EK_PHI], h->fld[EK_CHARGE], h->fld[EK_CHARGEN], h->dq, h->stream);
+        // E is only observable after the last solve (it is taken from the un-relaxed phi)
+        const bool last = (i == h->p.pb_iters - 1);
+        int n = 0;
+        st = ek_poisson_solve(h, h->poisson, c, h->dq, h->fld[EK_PHI], last ? h->fld[EK_EX] : nullptr,
+                              h->fld[EK_EY], h->fld[EK_EZ], h->stream, &n);      // LBM.cu:96
+        if (st != EK_OK) return st;
+        ek_launch_pbe_relax(c, h->p.PB_omega, h->fld[EK_PHI], h->phi_old, h->stream);  // LBM.cu:98-104
+    }
+    EK_CUDA(h, cudaGetLastError());
+    h->fields_ready = true;
+    h->pops_ready = false;
+    h->e_from_arrays = true;
+    return EK_OK;
+}
+
+ek_status ek_set_fields(ek_handle *h, const double *const fields[EK_NFIELDS], int src_on_device)
+{
+    if (!h || !fields) return EK_ERR_INVALID;
+    DeviceGuard g(h->device);
+    ek_status st = ek_alloc_state(h);
+    if (st != EK_OK) return st;
+    const EkConst &c = h->c;
+    for (int k = 0; k < EK_NFIELDS; ++k) {
+        if (!fields[k]) continue;
+        EK_CUDA(h, cudaMemcpy2DAsync(h->fld[k], (size_t)c.PX * sizeof(double), fields[k], (size_t)c.NX * sizeof(double),
+                                     (size_t)c.NX * sizeof(double), (size_t)c.NY * c.NZ,
+                                     src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+    }
+    EK_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->fields_ready = true;
+    h->pops_ready = false;
+    h->e_from_arrays = true;
+    return EK_OK;
+}
+
+ek_status ek_init_equilibrium(ek_handle *h)
+{
+    if (!h) return EK_ERR_INVALID;
+    if (!h->fields_ready) { ek_set_error(h, "ek_init_equilibrium before ek_init_fields/ek_set_fields"); return EK_ERR_STATE; }
+    DeviceGuard g(h->device);
+    h->cur = 0;
+    h->parity = 0;
+    StepArgs a = ek_step_args(h);
+    EK_CUDA(h, ek_launch_init_equilibrium(a, h->fld, h->stream));
+    dim3 b(128), gr((h->c.NX + 127) / 128, h->c.NY, h->c.NZ);
+    k_dq_from_fields<<<gr, b, 0, h->stream>>>(h->c, h->fld[EK_CHARGE], h->fld[EK_CHARGEN], h->dq);
+    EK_CUDA(h, cudaGetLastError());
+    h->pops_ready = true;
+    return EK_OK;
+}
+
+ek_status ek_init(ek_handle *h)
+{
+    ek_status st = ek_init_fields(h);
+    if (st != EK_OK) return st;
+    return ek_init_equilibrium(h);
+}
+
+ek_status ek_stream_collide_save(ek_handle *h, int write_fields)
+{
+    if (!h) return EK_ERR_INVALID;
+    if (!h->pops_ready) { ek_set_error(h, "ek_stream_collide_save before ek_init_equilibrium"); return EK_ERR_STATE; }
+    DeviceGuard g(h->device);
+    StepArgs a = ek_step_args(h);
+    const int mode = h->stream_mode == EK_STREAM_PUSH ? EK_MODE_PUSH : (h->parity ? EK_MODE_AA_ODD : EK_MODE_AA_EVEN);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h->profile) {
+        EK_CUDA(h, cudaEventCreate(&e0)); EK_CUDA(h, cudaEventCreate(&e1));
+        EK_CUDA(h, cudaEventRecord(e0, h->stream));
+    }
+    EK_CUDA(h, ek_launch_step(a, mode, write_fields != 0, h->e_from_arrays, h->stream));
+    if (h->profile) {
+        EK_CUDA(h, cudaEventRecord(e1, h->stream));
+        h->ev_lbm.emplace_back(e0, e1);
+    }
+    h->lbm_launches += 1;
+    if (h->stream_mode == EK_STREAM_PUSH) h->cur ^= 1; else h->parity ^= 1;
+    return EK_OK;
+}
+
+ek_status ek_fast_poisson(ek_handle *h, int write_efield)
+{
+    if (!h) return EK_ERR_INVALID;
+    if (!h->allocated) { ek_set_error(h, "ek_fast_poisson before initialisation"); return EK_ERR_STATE; }
+    DeviceGuard g(h->device);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h->profile) {
+        EK_CUDA(h, cudaEventCreate(&e0)); EK_CUDA(h, cudaEventCreate(&e1));
+        EK_CUDA(h, cudaEventRecord(e0, h->stream));
+    }
+    int n = 0;
+    ek_status st = ek_poisson_solve(h, h->poisson, h->c, h->dq, h->fld[EK_PHI], write_efield ? h->fld[EK_EX] : nullptr,
+                                    h->fld[EK_EY], h->fld[EK_EZ], h->stream, &n);
+    if (st != EK_OK) return st;
+    if (h->profile) {
+        EK_CUDA(h, cudaEventRecord(e1, h->stream));
+        h->ev_poi.emplace_back(e0, e1);
+    }
+    h->poisson_launches += n + 2;  // + the two cuFFT executions
+    h->e_from_arrays = false;      // from now on E = -grad(phi) of the fresh potential
+    h->efield_stale = !write_efield;
+    return EK_OK;
+}
+
+ek_status ek_step(ek_handle *h, int nsteps)
+{
+    if (!h || nsteps < 0) return EK_ERR_INVALID;
+    for (int i = 0; i < nsteps; ++i) {
+        const int full = (i == nsteps - 1);
+        ek_status st = ek_stream_collide_save(h, full);
+        if (st != EK_OK) return st;
+        st = ek_fast_poisson(h, full);
+        if (st != EK_OK) return st;
+        h->steps += 1;
+    }
+    return EK_OK;
+}
+
+ek_status ek_field_ptr(ek_handle *h, int id, double **dev_ptr)
+{
+    if (!h || !dev_ptr || id < 0 || id >= EK_NFIELDS) return EK_ERR_INVALID;
+    if (!h->allocated) return EK_ERR_STATE;
+    *dev_ptr = h->fld[id];
+    return EK_OK;
+}
+
+ek_status ek_get_field(ek_handle *h, int id, double *dst, int dst_on_device)
+{
+    if (!h || !dst || id < 0 || id >= EK_NFIELDS) return EK_ERR_INVALID;
+    if (!h->allocated) { ek_set_error(h, "ek_get_field before initialisation"); return EK_ERR_STATE; }
+    DeviceGuard g(h->device);
+    const EkConst &c = h->c;
+    if (id >= EK_EX && h->efield_stale) {
+        ek_launch_efield(c, h->fld[EK_PHI], h->fld[EK_EX], h->fld[EK_EY], h->fld[EK_EZ], h->stream);
+        h->efield_stale = false;
+    }
+    EK_CUDA(h, cudaMemcpy2DAsync(dst, (size_t)c.NX * sizeof(double), h->fld[id], (size_t)c.PX * sizeof(double),
+                                 (size_t)c.NX * sizeof(double), (size_t)c.NY * c.NZ,
+                                 dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+    EK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return EK_OK;
+}
+
+ek_status ek_get_populations(ek_handle *h, int set, double *dst, int dst_on_device)
+{
+    if (!h || !dst || set < 0 || set >= EK_NSETS) return EK_ERR_INVALID;
+    if (!h->pops_ready) { ek_set_error(h, "ek_get_populations before ek_init_equilibrium"); return EK_ERR_STATE; }
+    DeviceGuard g(h->device);
+    const size_t cells = (size_t)h->c.NX * h->c.NY * h->c.NZ;
+    StepArgs a = ek_step_args(h);
+    const int mode = (h->stream_mode == EK_STREAM_AA && h->parity) ? EK_MODE_AA_ODD : EK_MODE_AA_EVEN;
+    double *buf = dst;
+    if (!dst_on_device) EK_CUDA(h, cudaMalloc((void **)&buf, 27 * cells * sizeof(double)));
+    cudaError_t e = ek_launch_export(a, mode, set, buf, h->stream);
+    if (e == cudaSuccess && !dst_on_device)
+        e = cudaMemcpyAsync(dst, buf, 27 * cells * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (!dst_on_device) cudaFree(buf);
+    EK_CUDA(h, e);
+    return EK_OK;
+}
+
+}  // extern "C"

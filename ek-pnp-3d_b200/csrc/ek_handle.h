@@ -1,0 +1,44 @@
+// ek_handle.h -- the simulation handle behind the C ABI (one per device).
+#pragma once
+
+#include <new>
+#include <utility>
+#include <vector>
+
+#include "ek_internal.cuh"
+
+struct ek_handle {
+    ek_params p;
+    EkConst c;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // storage
+    int stream_mode = EK_STREAM_AA;
+    bool allocated = false;
+    double *lat[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
+    int cur = 0;            // PUSH: lattice holding the current state
+    int parity = 0;         // AA: 0 natural layout, 1 after an even step
+    double *wall = nullptr; // scalar-set wall state
+    double *fld[EK_NFIELDS] = {};
+    double *dq = nullptr;
+    double *phi_old = nullptr;
+    EkPoisson poisson;
+
+    // state machine
+    bool fields_ready = false;     // macroscopic arrays hold an initial state
+    bool pops_ready = false;       // populations initialised
+    bool e_from_arrays = false;    // next LBM pass takes E from the arrays, not from grad(phi)
+    bool efield_stale = false;     // Ex/Ey/Ez arrays are older than phi (recomputed on demand)
+    int zchunk = 8;
+
+    // counters / profiling
+    bool profile = false;
+    long long steps = 0, lbm_launches = 0, poisson_launches = 0;
+    double lbm_ms = 0.0, poisson_ms = 0.0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_lbm, ev_poi;
+};
+
+ek_status ek_alloc_state(ek_handle *h);
+StepArgs ek_step_args(ek_handle *h);

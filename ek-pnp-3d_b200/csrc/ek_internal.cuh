@@ -1,0 +1,140 @@
+// ek_internal.cuh -- shared definitions of the B200-native coupled step.
+//
+// Reference semantics followed here are cited as file:line relative to the
+// reference repository (gyf135/EK-PNP-3D); SURVEY.md App. A is the compact
+// numerical specification.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/ek_b200.h"
+
+// ---------------------------------------------------------------------------
+// D3Q27 velocity set (LBM.cu:872-1103, :639-644, :1983-2092).
+// Odd d and d+1 are opposite directions.
+// ---------------------------------------------------------------------------
+__host__ __device__ constexpr int ek_cx(int d)
+{
+    constexpr int t[27] = {0, 1,-1, 0, 0, 0, 0, 1,-1, 1,-1, 0, 0, 1,-1, 1,-1, 0, 0, 1,-1, 1,-1, 1,-1,-1, 1};
+    return t[d];
+}
+__host__ __device__ constexpr int ek_cy(int d)
+{
+    constexpr int t[27] = {0, 0, 0, 1,-1, 0, 0, 1,-1, 0, 0, 1,-1,-1, 1, 0, 0, 1,-1, 1,-1, 1,-1,-1, 1, 1,-1};
+    return t[d];
+}
+__host__ __device__ constexpr int ek_cz(int d)
+{
+    constexpr int t[27] = {0, 0, 0, 0, 0, 1,-1, 0, 0, 1,-1, 1,-1, 0, 0,-1, 1,-1, 1, 1,-1,-1, 1, 1,-1, 1,-1};
+    return t[d];
+}
+__host__ __device__ constexpr int ek_opp(int d) { return d == 0 ? 0 : ((d & 1) ? d + 1 : d - 1); }
+// weight class: 0 rest, 1 axis (ws), 2 face diagonal (wa), 3 cube diagonal (wd)
+__host__ __device__ constexpr int ek_wclass(int d) { return d == 0 ? 0 : (d <= 6 ? 1 : (d <= 18 ? 2 : 3)); }
+// moving-wall sign table of gpu_boundary (LBM.cu:1902-1927), asymmetries included
+__host__ __device__ constexpr int ek_uwsign(int d)
+{
+    constexpr int t[27] = {0, +1,-1, +1, 0, 0, 0, +1,-1, +1,-1, 0, 0, +1,-1, +1,-1, 0, 0, +1,-1, +1,-1, +1,-1, -1,+1};
+    return t[d];
+}
+
+enum { EK_MODE_AA_EVEN = 0, EK_MODE_AA_ODD = 1, EK_MODE_PUSH = 2 };
+
+// ---------------------------------------------------------------------------
+// Constants handed to every kernel by value.
+// ---------------------------------------------------------------------------
+struct EkConst {
+    int NX, NY, NZ;      // local grid
+    int PX;              // row pitch of every array (>= NX; ghost columns live in [NX, PX))
+    int xlo, xhi;        // column index of the x-1 neighbour of x=0 and of the x+1 neighbour of x=NX-1
+    long long plane;     // NY*PX
+    long long N;         // NZ*NY*PX : elements per direction slot / per field
+    double cflinv;       // 1/CFL                       (LBM.cu:1112)
+    double cflinv2;      // cflinv*cflinv/cs_square      (LBM.cu:1115)
+    double inv_cs2;      // 1/cs_square
+    double cs_square, CFL;
+    double tfac;         // 1/cs_square/CFL              (LBM.cu:854)
+    double dt;
+    double CtoC, Ext, exf, eps;
+    double rho0, Ra, nu, D;
+    double K, Kn;
+    double w[4];         // w0, ws, wa, wd              (LBM.h:109-112)
+    double coe[4];       // w/cs_square                  (LBM.cu:1107-1110)
+    double wp[4], wm[4]; // omega_plus*dt, omega_minus*dt per set (LBM.cu:488-495,1700-1707)
+    double sp, sm;       // 1 - dt*omega/2 for the fluid (LBM.cu:1660-1661)
+    double multi[4];     // moving-wall terms per class  (LBM.cu:1896-1898)
+    double twoTw[4];     // 2*TH*w per class             (LBM.cu:2226-2229)
+    double dx, dy, dz;
+    double voltage, voltage2;
+};
+
+struct StepArgs {
+    EkConst c;
+    double *in[4];        // population lattices, [27][N] per set
+    double *out[4];       // == in for the A-A scheme
+    double *wall;         // scalar-set wall state: [3 sets][2 planes][27][plane]
+    const double *phi;    // potential (E = -grad phi fused into the step)
+    const double *E[3];   // optional explicit field arrays (first step after init / shim)
+    double *dq;           // c+ - c- for the Poisson stage
+    double *fld[7];       // rho ux uy uz charge chargen T (only when fields are written)
+    int zchunk;
+};
+
+// ---------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------
+struct ek_handle;
+void ek_set_error(ek_handle *h, const std::string &msg);
+
+#define EK_CUDA(h, call)                                                        \
+    do {                                                                        \
+        cudaError_t _e = (call);                                                \
+        if (_e != cudaSuccess) {                                                \
+            ek_set_error((h), std::string(#call) + ": " + cudaGetErrorString(_e)); \
+            return EK_ERR_CUDA;                                                 \
+        }                                                                       \
+    } while (0)
+
+#define EK_CUFFT(h, call)                                                       \
+    do {                                                                        \
+        cufftResult _r = (call);                                                \
+        if (_r != CUFFT_SUCCESS) {                                              \
+            ek_set_error((h), std::string(#call) + ": cufft error " + std::to_string((int)_r)); \
+            return EK_ERR_CUFFT;                                                \
+        }                                                                       \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// Poisson stage (ek_poisson.cu)
+// ---------------------------------------------------------------------------
+struct EkPoisson {
+    int NX = 0, NY = 0, NZ = 0, NE = 0, NXH = 0, PX = 0;
+    cufftHandle plan_fwd = 0, plan_inv = 0;
+    bool plans = false;
+    double *real_ext = nullptr;          // [NE][NY][NX]
+    cufftDoubleComplex *spec = nullptr;  // [NE][NY][NXH]
+    double *kx2 = nullptr, *ky2 = nullptr, *kz_term = nullptr;  // device tables
+    void *work = nullptr;
+    size_t work_bytes = 0;
+};
+
+ek_status ek_poisson_create(ek_handle *h, EkPoisson &P, const ek_params &p, int PX, cudaStream_t st);
+void ek_poisson_destroy(EkPoisson &P);
+// dq = c+ - c-  ->  phi (and Ex,Ey,Ez when E != nullptr)
+ek_status ek_poisson_solve(ek_handle *h, EkPoisson &P, const EkConst &c, const double *dq, double *phi,
+                           double *Ex, double *Ey, double *Ez, cudaStream_t st, int *launches);
+void ek_launch_efield(const EkConst &c, const double *phi, double *Ex, double *Ey, double *Ez, cudaStream_t st);
+
+// ---------------------------------------------------------------------------
+// LBM stage (ek_lbm.cu) and start-up kernels (ek_init.cu)
+// ---------------------------------------------------------------------------
+cudaError_t ek_launch_step(const StepArgs &a, int mode, bool write_fields, bool e_from_arrays, cudaStream_t st);
+cudaError_t ek_launch_export(const StepArgs &a, int mode, int set, double *dst, cudaStream_t st);
+cudaError_t ek_launch_init_equilibrium(const StepArgs &a, const double *const fld[EK_NFIELDS], cudaStream_t st);
+void ek_launch_initialization(const EkConst &c, const ek_params &p, double *const fld[EK_NFIELDS], cudaStream_t st);
+void ek_launch_pbe(const EkConst &c, const ek_params &p, const double *phi, double *charge, double *chargen,
+                   double *dq, cudaStream_t st);
+void ek_launch_pbe_relax(const EkConst &c, double omega, double *phi, double *phi_old, cudaStream_t st);

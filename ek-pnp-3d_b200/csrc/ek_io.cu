@@ -1,0 +1,172 @@
+// ek_io.cu -- diagnostics and field dumps in the reference's formats.
+//
+// Replaces current() (LBM.cu:2674-2710), the reduction of record_umax()
+// (LBM.cu:2712-2753), save_data_tecplot() (LBM.cu:2492-2565) and
+// save_data_end() (LBM.cu:2567-2627).  The diagnostics are device reductions
+// (the reference copies three full fields to the host for each); the dumps
+// keep the reference's text formats, including the dump-time linear
+// extrapolation of rho, c+, c-, u onto the wall planes (LBM.cu:2527-2542).
+#include <stdio.h>
+
+#include <vector>
+
+#include "ek_handle.h"
+
+namespace {
+
+// per-row partial sums of (c+ - c-)*Ez on the top plane, charges extrapolated
+__global__ void k_wall_current(EkConst c, const double *ch, const double *chn, const double *ez, double *partial)
+{
+    const int y = blockIdx.x;
+    __shared__ double sh[128];
+    double acc = 0.0;
+    for (int x = threadIdx.x; x < c.NX; x += blockDim.x) {
+        const size_t col = (size_t)y * c.PX + x;
+        const size_t i1 = (size_t)(c.NZ - 1) * c.plane + col, i2 = (size_t)(c.NZ - 2) * c.plane + col,
+                     i3 = (size_t)(c.NZ - 3) * c.plane + col;
+        const double ct = 2.0 * ch[i2] - ch[i3];
+        const double cnt = 2.0 * chn[i2] - chn[i3];
+        acc += (ct - cnt) * ez[i1];
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[y] = sh[0];
+}
+
+__global__ void k_max_uz(EkConst c, const double *uz, double *partial)
+{
+    const int y = blockIdx.x, z = blockIdx.y;
+    __shared__ double sh[128];
+    double m = 0.0;
+    for (int x = threadIdx.x; x < c.NX; x += blockDim.x) m = fmax(m, uz[(size_t)z * c.plane + (size_t)y * c.PX + x]);
+    sh[threadIdx.x] = m;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sh[threadIdx.x] = fmax(sh[threadIdx.x], sh[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[(size_t)z * c.NY + y] = sh[0];
+}
+
+struct HostFields {
+    std::vector<double> f[EK_NFIELDS];
+};
+
+ek_status fetch_all(ek_handle *h, HostFields &H)
+{
+    const size_t cells = (size_t)h->c.NX * h->c.NY * h->c.NZ;
+    for (int k = 0; k < EK_NFIELDS; ++k) {
+        H.f[k].resize(cells);
+        ek_status st = ek_get_field(h, k, H.f[k].data(), 0);
+        if (st != EK_OK) return st;
+    }
+    // LBM.cu:2527-2542
+    const int NX = h->c.NX, NY = h->c.NY, NZ = h->c.NZ;
+    auto idx = [&](int x, int y, int z) { return (size_t)NX * ((size_t)NY * z + y) + x; };
+    const int ext[6] = {EK_RHO, EK_CHARGE, EK_CHARGEN, EK_UX, EK_UY, EK_UZ};
+    for (int y = 0; y < NY; ++y)
+        for (int x = 0; x < NX; ++x)
+            for (int k = 0; k < 6; ++k) {
+                std::vector<double> &a = H.f[ext[k]];
+                a[idx(x, y, 0)] = 2.0 * a[idx(x, y, 1)] - a[idx(x, y, 2)];
+                a[idx(x, y, NZ - 1)] = 2.0 * a[idx(x, y, NZ - 2)] - a[idx(x, y, NZ - 3)];
+            }
+    return EK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+ek_status ek_wall_current(ek_handle *h, double *current)
+{
+    if (!h || !current) return EK_ERR_INVALID;
+    if (!h->allocated) return EK_ERR_STATE;
+    const EkConst &c = h->c;
+    if (h->efield_stale) {
+        ek_launch_efield(c, h->fld[EK_PHI], h->fld[EK_EX], h->fld[EK_EY], h->fld[EK_EZ], h->stream);
+        h->efield_stale = false;
+    }
+    double *partial = nullptr;
+    EK_CUDA(h, cudaMalloc((void **)&partial, c.NY * sizeof(double)));
+    k_wall_current<<<c.NY, 128, 0, h->stream>>>(c, h->fld[EK_CHARGE], h->fld[EK_CHARGEN], h->fld[EK_EZ], partial);
+    std::vector<double> host(c.NY);
+    cudaError_t e = cudaMemcpyAsync(host.data(), partial, c.NY * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(partial);
+    EK_CUDA(h, e);
+    double I = 0;
+    for (int y = 0; y < c.NY; ++y) I += host[y];
+    *current = I * h->p.K * h->p.dz * h->p.dz;  // LBM.cu:2708
+    return EK_OK;
+}
+
+ek_status ek_max_uz(ek_handle *h, double *umax)
+{
+    if (!h || !umax) return EK_ERR_INVALID;
+    if (!h->allocated) return EK_ERR_STATE;
+    const EkConst &c = h->c;
+    const size_t n = (size_t)c.NY * c.NZ;
+    double *partial = nullptr;
+    EK_CUDA(h, cudaMalloc((void **)&partial, n * sizeof(double)));
+    k_max_uz<<<dim3(c.NY, c.NZ), 128, 0, h->stream>>>(c, h->fld[EK_UZ], partial);
+    std::vector<double> host(n);
+    cudaError_t e = cudaMemcpyAsync(host.data(), partial, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(partial);
+    EK_CUDA(h, e);
+    double m = 0;  // LBM.cu:2717: starts from 0
+    for (size_t i = 0; i < n; ++i) m = host[i] > m ? host[i] : m;
+    *umax = m;
+    return EK_OK;
+}
+
+ek_status ek_save_data_tecplot(ek_handle *h, const char *path, double time, int append, int first)
+{
+    if (!h || !path) return EK_ERR_INVALID;
+    HostFields H;
+    ek_status st = fetch_all(h, H);
+    if (st != EK_OK) return st;
+    FILE *f = fopen(path, append ? "ab" : "wb");
+    if (!f) { ek_set_error(h, std::string("cannot open ") + path); return EK_ERR_INVALID; }
+    const int NX = h->c.NX, NY = h->c.NY, NZ = h->c.NZ;
+    if (first)
+        fprintf(f, "%s\n",
+                "VARIABLES=\"x\",\"y\",\"z\",\"u\",\"v\",\"w\",\"p\",\"charge\",\"neg charge\",\"phi\",\"Ex\",\"Ey\",\"Ez\",\"Temperature\"");
+    fprintf(f, "\n");
+    fprintf(f, "ZONE T=\"t=%g\", F=POINT, I = %d, J = %d, K = %d\n", time, NX, NY, NZ);
+    for (int z = 0; z < NZ; ++z)
+        for (int y = 0; y < NY; ++y)
+            for (int x = 0; x < NX; ++x) {
+                const size_t i = (size_t)NX * ((size_t)NY * z + y) + x;
+                fprintf(f, "%g %g %g %g %g %g %g %g %10.6f %10.6f %10.6f %10.6f %10.6f %10.6f\n", h->p.dx * x,
+                        h->p.dy * y, h->p.dz * z, H.f[EK_UX][i], H.f[EK_UY][i], H.f[EK_UZ][i], H.f[EK_RHO][i],
+                        H.f[EK_CHARGE][i], H.f[EK_CHARGEN][i], H.f[EK_PHI][i], H.f[EK_EX][i], H.f[EK_EY][i],
+                        H.f[EK_EZ][i], H.f[EK_T][i]);
+            }
+    fclose(f);
+    return EK_OK;
+}
+
+ek_status ek_save_data_end(ek_handle *h, const char *path, double time)
+{
+    if (!h || !path) return EK_ERR_INVALID;
+    HostFields H;
+    ek_status st = fetch_all(h, H);
+    if (st != EK_OK) return st;
+    FILE *f = fopen(path, "wb");
+    if (!f) { ek_set_error(h, std::string("cannot open ") + path); return EK_ERR_INVALID; }
+    const size_t cells = (size_t)h->c.NX * h->c.NY * h->c.NZ;
+    for (size_t i = 0; i < cells; ++i)
+        fprintf(f, "%10.6f %10.6f %10.6f %10.6f %10.6f %10.6f %10.6f %10.6f %10.6f %10.6f %10.6f %10.6f\n", time,
+                H.f[EK_UX][i], H.f[EK_UY][i], H.f[EK_UZ][i], H.f[EK_RHO][i], H.f[EK_CHARGE][i], H.f[EK_CHARGEN][i],
+                H.f[EK_PHI][i], H.f[EK_EX][i], H.f[EK_EY][i], H.f[EK_EZ][i], H.f[EK_T][i]);
+    fclose(f);
+    return EK_OK;
+}
+
+}  // extern "C"

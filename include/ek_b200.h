@@ -1,0 +1,144 @@
+/*
+ * ek_b200.h -- C ABI of the B200-native coupled electrokinetic time step.
+ *
+ * Drop-in boundary for the simulation loop of gyf135/EK-PNP-3D
+ * (main.cu:189-224): D3Q27 TRT lattice-Boltzmann fluid + cation + anion +
+ * temperature, coupled to the spectral Poisson solve.  Plain pointers and
+ * sizes only; every entry point returns an ek_status instead of calling
+ * exit() as the reference does (LBM.cu:35-53, LBM.h:187-208).
+ *
+ * "Replaces" cites the reference interface each entry point stands in for
+ * (paths relative to the reference repository).
+ *
+ * Threading: one handle = one simulation on one CUDA device; a handle is not
+ * thread-safe (the reference is single-threaded, default stream only).
+ */
+#ifndef EK_B200_H
+#define EK_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EK_B200_ABI_VERSION 1
+
+typedef enum ek_status {
+    EK_OK = 0,
+    EK_ERR_INVALID = 1,   /* bad argument / unsupported grid */
+    EK_ERR_CUDA = 2,      /* CUDA runtime error (see ek_last_error) */
+    EK_ERR_CUFFT = 3,     /* cuFFT error */
+    EK_ERR_STATE = 4,     /* call out of order (e.g. step before init) */
+    EK_ERR_NOMEM = 5
+} ek_status;
+
+/* Input parameters.  Replaces the compile-time constants of LBM.h:29-125
+ * (SURVEY.md App. B); same names, same meaning, now runtime values.
+ * NX is the fastest-varying index of every array (LBM.cu:17-30). */
+typedef struct ek_params {
+    int NX, NY, NZ;                  /* LBM.h:32-35; z includes both wall planes */
+    double Lx, Ly, Lz;               /* LBM.h:40-42; must be NX*dx, NY*dy, (NZ-1)*dz */
+    double dx, dy, dz;               /* LBM.h:43-45 */
+    double uw, exf;                  /* LBM.h:47-50 top-wall speed, body force along x */
+    double CFL, dt, cs_square, rho0; /* LBM.h:51-54 */
+    double chargeinf;                /* LBM.h:56 bulk concentration */
+    double voltage, voltage2;        /* LBM.h:60,62 wall (zeta) potentials, z=0 / z=NZ-1 */
+    double Ext, eps;                 /* LBM.h:64-65 external field along x, permittivity */
+    double diffu, nu, K;             /* LBM.h:66-70 cation diffusivity, viscosity, cation mobility */
+    double diffun, Kn;               /* LBM.h:73-76 anion diffusivity and mobility */
+    double kB, electron, roomT, convertCtoCharge, PB_omega; /* LBM.h:87-91 */
+    double D, Ra, TH;                /* LBM.h:95-98 thermal diffusivity, buoyancy coefficient, bottom temperature */
+    double w0, ws, wa, wd;           /* LBM.h:109-112 D3Q27 weights */
+    double V, VC, VCn, VT;           /* LBM.h:115-118 TRT magic products */
+    int pb_iters;                    /* LBM.cu:89 Poisson-Boltzmann start-up iterations (501) */
+} ek_params;
+
+/* Macroscopic arrays, N = NX*NY*NZ doubles each, index NX*(NY*z+y)+x
+ * (LBM.cu:22-25): the reference's dump contract (LBM.cu:2511-2521). */
+typedef enum ek_field {
+    EK_RHO = 0, EK_UX, EK_UY, EK_UZ, EK_CHARGE, EK_CHARGEN,
+    EK_PHI, EK_T, EK_EX, EK_EY, EK_EZ, EK_NFIELDS
+} ek_field;
+
+/* population sets, in the order of the reference's arrays f, h, hn, temp */
+typedef enum ek_set { EK_FLUID = 0, EK_CATION, EK_ANION, EK_TEMPERATURE, EK_NSETS } ek_set;
+
+/* streaming schemes (ek_set_option "stream_mode") */
+#define EK_STREAM_AA 0    /* in-place A-A pattern, one lattice (default)      */
+#define EK_STREAM_PUSH 1  /* two lattices, collide-and-push                    */
+
+typedef struct ek_handle ek_handle;
+
+/* LBM.h as shipped (50x8x51 microchannel). */
+void ek_default_params(ek_params *p);
+
+/* Replaces main.cu:58-152 (device selection, 27 cudaMallocs, cuFFT plan,
+ * wavenumber tables).  device < 0 keeps the current device. */
+ek_status ek_create(const ek_params *p, int device, ek_handle **out);
+/* Replaces main.cu:259-291. */
+ek_status ek_destroy(ek_handle *h);
+
+/* Replaces initialization() (LBM.h:159, LBM.cu:68-146): uniform state, then
+ * pb_iters under-relaxed Poisson-Boltzmann iterations, entirely on device. */
+ek_status ek_init_fields(ek_handle *h);
+/* Replaces read_data()'s upload (LBM.cu:2629-2671) / a caller-made state:
+ * fields[id] may be NULL to keep the current array.  src_on_device selects
+ * cudaMemcpy direction. */
+ek_status ek_set_fields(ek_handle *h, const double *const fields[EK_NFIELDS], int src_on_device);
+/* Replaces init_equilibrium() (LBM.h:162, LBM.cu:150-463): populations of
+ * the four sets from rho,u,c+,c-,T and E. */
+ek_status ek_init_equilibrium(ek_handle *h);
+/* ek_init_fields + ek_init_equilibrium: the reference's start of run with
+ * flag == 0 (main.cu:165-174). */
+ek_status ek_init(ek_handle *h);
+
+/* nsteps iterations of main.cu:189-200: stream_collide_save() (LBM.h:165,
+ * LBM.cu:465-481) followed by fast_Poisson() (LBM.h:176, poisson.cu:75-103).
+ * Asynchronous on the handle's stream.  After it returns (and ek_sync) the
+ * eleven macroscopic arrays hold what the reference's arrays hold after the
+ * same number of loop iterations. */
+ek_status ek_step(ek_handle *h, int nsteps);
+/* The two halves separately (same contract as the reference functions):
+ * one LBM pass that leaves c+ - c- for the solver, then the solve. */
+ek_status ek_stream_collide_save(ek_handle *h, int write_fields);
+ek_status ek_fast_poisson(ek_handle *h, int write_efield);
+
+ek_status ek_sync(ek_handle *h);
+
+/* Replaces the cudaMemcpy D2H calls of save_data_tecplot/current/record_umax
+ * (LBM.cu:2511-2521, main.cu:212-214, LBM.cu:2720-2722). */
+ek_status ek_get_field(ek_handle *h, int id, double *dst, int dst_on_device);
+/* Device pointer of a macroscopic array (owned by the handle). */
+ek_status ek_field_ptr(ek_handle *h, int id, double **dev_ptr);
+/* Pre-collision populations of one set in the reference's layout:
+ * 27*N doubles, [d][z][y][x], d = 0 the rest population (f0|f1 of
+ * LBM.cu:17-30 back to back).  For tests. */
+ek_status ek_get_populations(ek_handle *h, int set, double *dst, int dst_on_device);
+
+/* options: "stream_mode" (EK_STREAM_*; before ek_init*), "zchunk",
+ * "profile" (1: time every LBM/Poisson launch with CUDA events). */
+ek_status ek_set_option(ek_handle *h, const char *key, long long value);
+/* counters: "steps", "lbm_launches", "poisson_launches", "kernel_launches";
+ * times (ms, profile on): "lbm_ms", "poisson_ms" */
+ek_status ek_get_counter(ek_handle *h, const char *key, double *value);
+ek_status ek_reset_counters(ek_handle *h);
+
+/* cudaStream_t of the handle, as void*. */
+void *ek_stream(ek_handle *h);
+const char *ek_last_error(ek_handle *h);
+int ek_abi_version(void);
+
+/* Diagnostics on device.  Replace current() (LBM.cu:2674-2710) and the
+ * reduction of record_umax() (LBM.cu:2712-2753). */
+ek_status ek_wall_current(ek_handle *h, double *current);
+ek_status ek_max_uz(ek_handle *h, double *umax);
+
+/* Field dumps in the reference's formats (LBM.cu:2492-2627), including the
+ * dump-time wall extrapolation of LBM.cu:2527-2542.  first != 0 writes the
+ * VARIABLES header. */
+ek_status ek_save_data_tecplot(ek_handle *h, const char *path, double time, int append, int first);
+ek_status ek_save_data_end(ek_handle *h, const char *path, double time);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EK_B200_H */

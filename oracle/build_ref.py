@@ -1,0 +1,147 @@
+#!/usr/bin/env python3
+"""Build the reference's own CUDA code into oracle/_ref/ (TEST INFRASTRUCTURE).
+
+The reference (gyf135/EK-PNP-3D, mounted read-only at /root/reference) has no
+build system and no runtime parameters: every input is a compile-time constant
+in LBM.h.  This recipe therefore
+
+  * regenerates LBM.h per case in a scratch directory by rewriting only the
+    constant initialisers listed in CASES (regex on the declaration lines),
+  * compiles oracle/ref_driver.cu, which #includes that header and then the
+    reference's LBM.cu and poisson.cu from where they lie (-I /root/reference),
+  * writes nothing but binaries and a manifest into oracle/_ref/.
+
+No reference source is copied into the repository.  /root/reference does not
+exist on the GPU box, so this runs in the build container only (it is called
+from __graft_entry__.build()); the binaries travel with the snapshot.
+
+Also built: ek_ref_stock = the UNMODIFIED main.cu + seconds.cpp, for the
+"as shipped, I/O included" timing of config C1.
+"""
+from __future__ import annotations
+
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("EK_REFERENCE_DIR", "/root/reference")
+OUT = os.path.join(HERE, "_ref")
+ARCH = ["-gencode", "arch=compute_100,code=sm_100"]
+
+DX = 1.0e-6 / 100.0
+
+# name -> overrides of LBM.h symbols.  Lx/Ly/Lz follow the grid (App. B).
+CASES = {
+    # C1: the shipped case (LBM.h untouched except nothing) -- 50x8x51, nThreads 10
+    "c1": dict(NX=50, NY=8, NZ=51, nThreads=10),
+    # small parity grids (perturbation applied at run time by the driver)
+    "g1": dict(NX=16, NY=8, NZ=13, nThreads=16),
+    "g2": dict(NX=32, NY=16, NZ=17, nThreads=32),
+    "g2_nofmad": dict(NX=32, NY=16, NZ=17, nThreads=32, _nvcc=["-fmad=false"]),
+    # moving top wall + pressure drive + asymmetric zeta potentials
+    "g3": dict(NX=24, NY=8, NZ=11, nThreads=24, uw_host=1.0e-4, exf_host=2.0e6,
+               voltage2=-2.5e-3),
+    # C2: isothermal electro-osmotic slit flow 128x64x64 (TH = 0 -> T == 0)
+    "c2": dict(NX=128, NY=64, NZ=64, nThreads=128, TH=0.0),
+    # C3: EK-PNP + temperature coupling 256^3
+    "c3": dict(NX=256, NY=256, NZ=256, nThreads=128),
+    "c3_t64": dict(NX=256, NY=256, NZ=256, nThreads=64),
+    "c3_t256": dict(NX=256, NY=256, NZ=256, nThreads=256),
+}
+
+# symbol -> (regex matching "<decl> = <value>;", formatter)
+_DECL = {
+    "nThreads": r"(const int nThreads\s*=\s*)([^;]+)(;)",
+    "NX": r"(const unsigned int NX\s*=\s*)([^;]+)(;)",
+    "NY": r"(const unsigned int NY\s*=\s*)([^;]+)(;)",
+    "NZ": r"(const unsigned int NZ\s*=\s*)([^;]+)(;)",
+    "Lx": r"(__constant__ double Lx\s*=\s*)([^;]+)(;)",
+    "Ly": r"(__constant__ double Ly\s*=\s*)([^;]+)(;)",
+    "Lz": r"(__constant__ double Lz\s*=\s*)([^;]+)(;)",
+    "uw_host": r"(double uw_host\s*=\s*)([^;]+)(;)",
+    "exf_host": r"(double exf_host\s*=\s*)([^;]+)(;)",
+    "voltage": r"(__constant__ double voltage\s*=\s*)([^;]+)(;)",
+    "voltage2": r"(__constant__ double voltage2\s*=\s*)([^;]+)(;)",
+    "Ext": r"(__constant__ double Ext\s*=\s*)([^;]+)(;)",
+    "TH": r"(__device__ double TH\s*=\s*)([^;]+)(;)",
+    "Ra": r"(__device__ double Ra\s*=\s*)([^;]+)(;)",
+}
+
+
+def case_params(name: str) -> dict:
+    """Full symbol->value map written into the generated header for a case."""
+    c = {k: v for k, v in CASES[name].items() if not k.startswith("_")}
+    c.setdefault("Lx", c["NX"] * DX)
+    c.setdefault("Ly", c["NY"] * DX)
+    c.setdefault("Lz", (c["NZ"] - 1) * DX)
+    return c
+
+
+def patched_header(name: str) -> str:
+    with open(os.path.join(REF, "LBM.h")) as f:
+        text = f.read()
+    for sym, val in case_params(name).items():
+        pat = _DECL[sym]
+        lit = str(int(val)) if sym in ("nThreads", "NX", "NY", "NZ") else repr(float(val))
+        text, n = re.subn(pat, lambda m: m.group(1) + lit + m.group(3), text, count=1)
+        if n != 1:
+            raise RuntimeError(f"could not rewrite {sym} in LBM.h")
+    return text
+
+
+def build_case(name: str, verbose: bool = False) -> str:
+    os.makedirs(OUT, exist_ok=True)
+    exe = os.path.join(OUT, f"ek_ref_{name}")
+    with tempfile.TemporaryDirectory(prefix="ekref_") as tmp:
+        with open(os.path.join(tmp, "LBM.h"), "w") as f:
+            f.write(patched_header(name))
+        cmd = ["nvcc", "-O3", "-w", *ARCH, *CASES[name].get("_nvcc", []),
+               "-I", tmp, "-I", REF, os.path.join(HERE, "ref_driver.cu"),
+               "-lcufft", "-o", exe]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+    return exe
+
+
+def build_stock() -> str:
+    """The reference exactly as shipped (main.cu + seconds.cpp)."""
+    os.makedirs(OUT, exist_ok=True)
+    exe = os.path.join(OUT, "ek_ref_stock")
+    cmd = ["nvcc", "-O3", "-w", *ARCH, os.path.join(REF, "main.cu"),
+           os.path.join(REF, "seconds.cpp"), "-lcufft", "-o", exe]
+    subprocess.check_call(cmd)
+    return exe
+
+
+def main(argv):
+    if not os.path.isdir(REF):
+        print(f"{REF} not present: nothing to build (prebuilt binaries are used)")
+        return 0
+    names = argv[1:] or list(CASES)
+    manifest = {}
+    if not argv[1:]:
+        build_stock()
+        manifest["stock"] = {"binary": "ek_ref_stock", "note": "unmodified main.cu"}
+    for n in names:
+        build_case(n, verbose=True)
+        manifest[n] = {"binary": f"ek_ref_{n}", "params": case_params(n),
+                       "nvcc": CASES[n].get("_nvcc", [])}
+    mpath = os.path.join(OUT, "manifest.json")
+    old = {}
+    if os.path.exists(mpath):
+        with open(mpath) as f:
+            old = json.load(f)
+    old.update(manifest)
+    with open(mpath, "w") as f:
+        json.dump(old, f, indent=1)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main(sys.argv))
