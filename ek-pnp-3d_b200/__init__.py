@@ -24,6 +24,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "ek_b200.h")
 FIELDS = ("rho", "ux", "uy", "uz", "charge", "chargen", "phi", "T", "Ex", "Ey", "Ez")
 SETS = ("fluid", "cation", "anion", "temperature")
 STREAM_AA, STREAM_PUSH = 0, 1
+DC_ZERO, DC_LITERAL, DC_PRESCRIBED = 0, 1, 2
 
 _STATUS = {0: "EK_OK", 1: "EK_ERR_INVALID", 2: "EK_ERR_CUDA", 3: "EK_ERR_CUFFT", 4: "EK_ERR_STATE", 5: "EK_ERR_NOMEM"}
 
@@ -85,6 +86,7 @@ def load_library():
     L.ek_field_ptr.argtypes = [H, C.c_int, C.POINTER(C.c_void_p)]
     L.ek_get_populations.argtypes = [H, C.c_int, C.c_void_p, C.c_int]
     L.ek_set_option.argtypes = [H, C.c_char_p, C.c_longlong]
+    L.ek_set_poisson_dc.argtypes = [H, C.c_int, C.c_double]
     L.ek_get_counter.argtypes = [H, C.c_char_p, C.POINTER(C.c_double)]
     L.ek_stream.argtypes = [H]
     L.ek_stream.restype = C.c_void_p
@@ -162,6 +164,10 @@ class Simulation:
 
     def set_option(self, key: str, value: int):
         self._ck(self.L.ek_set_option(self.h, key.encode(), int(value)), f"ek_set_option({key})")
+
+    def set_poisson_dc(self, mode: int, ghat0: float = 0.0):
+        """DC mode of the Poisson right-hand side (see ek_b200.h)."""
+        self._ck(self.L.ek_set_poisson_dc(self.h, int(mode), float(ghat0)), "ek_set_poisson_dc")
 
     def counter(self, key: str) -> float:
         v = C.c_double()

@@ -239,6 +239,14 @@ ek_status ek_set_option(ek_handle *h, const char *key, long long value)
     return EK_ERR_INVALID;
 }
 
+ek_status ek_set_poisson_dc(ek_handle *h, int mode, double ghat0)
+{
+    if (!h || mode < EK_DC_ZERO || mode > EK_DC_PRESCRIBED) return EK_ERR_INVALID;
+    h->dc_mode = mode;
+    h->dc_ghat0 = ghat0;
+    return EK_OK;
+}
+
 ek_status ek_sync(ek_handle *h)
 {
     if (!h) return EK_ERR_INVALID;
@@ -291,7 +299,7 @@ ek_status ek_init_fields(ek_handle *h)
         const bool last = (i == h->p.pb_iters - 1);
         int n = 0;
         st = ek_poisson_solve(h, h->poisson, c, h->dq, h->fld[EK_PHI], last ? h->fld[EK_EX] : nullptr,
-                              h->fld[EK_EY], h->fld[EK_EZ], h->stream, &n);      // LBM.cu:96
+                              h->fld[EK_EY], h->fld[EK_EZ], h->dc_mode, h->dc_ghat0, h->stream, &n);  // LBM.cu:96
         if (st != EK_OK) return st;
         ek_launch_pbe_relax(c, h->p.PB_omega, h->fld[EK_PHI], h->phi_old, h->stream);  // LBM.cu:98-104
     }
@@ -379,7 +387,7 @@ ek_status ek_fast_poisson(ek_handle *h, int write_efield)
     }
     int n = 0;
     ek_status st = ek_poisson_solve(h, h->poisson, h->c, h->dq, h->fld[EK_PHI], write_efield ? h->fld[EK_EX] : nullptr,
-                                    h->fld[EK_EY], h->fld[EK_EZ], h->stream, &n);
+                                    h->fld[EK_EY], h->fld[EK_EZ], h->dc_mode, h->dc_ghat0, h->stream, &n);
     if (st != EK_OK) return st;
     if (h->profile) {
         EK_CUDA(h, cudaEventRecord(e1, h->stream));

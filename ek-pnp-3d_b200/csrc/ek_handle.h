@@ -32,6 +32,8 @@ struct ek_handle {
     bool e_from_arrays = false;    // next LBM pass takes E from the arrays, not from grad(phi)
     bool efield_stale = false;     // Ex/Ey/Ez arrays are older than phi (recomputed on demand)
     int zchunk = 8;
+    int dc_mode = EK_DC_ZERO;
+    double dc_ghat0 = 0.0;
 
     // counters / profiling
     bool profile = false;

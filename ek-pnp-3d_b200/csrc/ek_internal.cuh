@@ -125,7 +125,8 @@ ek_status ek_poisson_create(ek_handle *h, EkPoisson &P, const ek_params &p, int 
 void ek_poisson_destroy(EkPoisson &P);
 // dq = c+ - c-  ->  phi (and Ex,Ey,Ez when E != nullptr)
 ek_status ek_poisson_solve(ek_handle *h, EkPoisson &P, const EkConst &c, const double *dq, double *phi,
-                           double *Ex, double *Ey, double *Ez, cudaStream_t st, int *launches);
+                           double *Ex, double *Ey, double *Ez, int dc_mode, double dc_ghat0, cudaStream_t st,
+                           int *launches);
 void ek_launch_efield(const EkConst &c, const double *phi, double *Ex, double *Ey, double *Ez, cudaStream_t st);
 
 // ---------------------------------------------------------------------------

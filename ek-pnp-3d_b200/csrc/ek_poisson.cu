@@ -44,7 +44,7 @@ __global__ void k_pack_odd(EkConst c, int NE, const double *__restrict__ dq, dou
 
 // gpu_derivative (poisson.cu:169-180) on the half spectrum
 __global__ void k_divide(int NXH, int NY, const double *__restrict__ kx, const double *__restrict__ ky,
-                         const double *__restrict__ kzterm, cufftDoubleComplex *spec)
+                         const double *__restrict__ kzterm, cufftDoubleComplex *spec, int dc_mode, double dc_ghat0)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= NXH) return;
@@ -54,6 +54,11 @@ __global__ void k_divide(int NXH, int NY, const double *__restrict__ kx, const d
     if (y == 0 && x == 0 && z == 0) mu = 1.0;
     const size_t i = ((size_t)z * NY + y) * NXH + x;
     cufftDoubleComplex v = spec[i];
+    if (y == 0 && x == 0 && z == 0) {
+        // zero by oddness; see ek_set_poisson_dc() in ek_b200.h
+        if (dc_mode == EK_DC_ZERO) { v.x = 0.0; v.y = 0.0; }
+        else if (dc_mode == EK_DC_PRESCRIBED) { v.x = dc_ghat0; v.y = 0.0; }
+    }
     v.x = -v.x / mu;
     v.y = -v.y / mu;
     spec[i] = v;
@@ -137,13 +142,14 @@ void ek_poisson_destroy(EkPoisson &P)
 }
 
 ek_status ek_poisson_solve(ek_handle *h, EkPoisson &P, const EkConst &c, const double *dq, double *phi,
-                           double *Ex, double *Ey, double *Ez, cudaStream_t st, int *launches)
+                           double *Ex, double *Ey, double *Ez, int dc_mode, double dc_ghat0, cudaStream_t st,
+                           int *launches)
 {
     dim3 b(128);
     dim3 ge((c.NX + 127) / 128, c.NY, P.NE), gs((P.NXH + 127) / 128, c.NY, P.NE), gz((c.NX + 127) / 128, c.NY, c.NZ);
     k_pack_odd<<<ge, b, 0, st>>>(c, P.NE, dq, P.real_ext, c.eps);
     EK_CUFFT(h, cufftExecD2Z(P.plan_fwd, P.real_ext, P.spec));
-    k_divide<<<gs, b, 0, st>>>(P.NXH, c.NY, P.kx2, P.ky2, P.kz_term, P.spec);
+    k_divide<<<gs, b, 0, st>>>(P.NXH, c.NY, P.kx2, P.ky2, P.kz_term, P.spec, dc_mode, dc_ghat0);
     EK_CUFFT(h, cufftExecZ2D(P.plan_inv, P.spec, P.real_ext));
     const double size = (double)((unsigned int)c.NX * (unsigned int)c.NY * (unsigned int)P.NE);  // LBM.h:38
     k_unpack<<<gz, b, 0, st>>>(c, P.real_ext, size, phi);

@@ -114,6 +114,20 @@ ek_status ek_field_ptr(ek_handle *h, int id, double **dev_ptr);
  * LBM.cu:17-30 back to back).  For tests. */
 ek_status ek_get_populations(ek_handle *h, int set, double *dst, int dst_on_device);
 
+/* The (kx,ky,kz) = (0,0,0) mode of the extended right-hand side.  It is zero
+ * by oddness in exact arithmetic; the reference divides whatever rounding
+ * residue its cuFFT Z2Z leaves there by mu := 1 (poisson.cu:176-177) while
+ * every other mode is divided by mu ~ 1e15, i.e. it adds an
+ * implementation-dependent constant to the interior potential (DESIGN.md,
+ * "DC artefact").  EK_DC_ZERO (default) enforces the exact value 0;
+ * EK_DC_LITERAL keeps this library's own residue with mu = 1;
+ * EK_DC_PRESCRIBED uses ghat0 as the forward coefficient (test hook: replay
+ * the residue recorded from a reference run). */
+#define EK_DC_ZERO 0
+#define EK_DC_LITERAL 1
+#define EK_DC_PRESCRIBED 2
+ek_status ek_set_poisson_dc(ek_handle *h, int mode, double ghat0);
+
 /* options: "stream_mode" (EK_STREAM_*; before ek_init*), "zchunk",
  * "profile" (1: time every LBM/Poisson launch with CUDA events). */
 ek_status ek_set_option(ek_handle *h, const char *key, long long value);

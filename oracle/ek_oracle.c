@@ -40,6 +40,9 @@ struct eko_state {
     double *kx, *ky, *kz;
     double *ext;       /* complex scratch, interleaved, NX*NY*NE */
     double *phi_old;
+    int dc_mode;       /* 0 zero, 1 literal (reference, default), 2 prescribed */
+    double dc_ghat0;
+    double last_dc;    /* forward DC coefficient seen by the last solve */
 };
 
 /* ---- index helpers: LBM.cu:17-30 ---- */
@@ -104,6 +107,7 @@ eko_state *eko_create(const eko_params *p)
     s->kz = (double *)malloc(sizeof(double) * s->NE);
     s->ext = (double *)malloc(sizeof(double) * 2 * (size_t)p->NX * p->NY * s->NE);
     s->phi_old = (double *)calloc(s->N, sizeof(double));
+    s->dc_mode = 1;
     /* main.cu:119-145 (unsigned loop indices; "(double)i - NX") */
     const int NX = p->NX, NY = p->NY, NE = s->NE;
     for (int i = 0; i <= NX / 2; i++) s->kx[i] = (double)i * 2.0 * M_PI / p->Lx;
@@ -125,6 +129,9 @@ void eko_destroy(eko_state *s)
 }
 
 double *eko_field(eko_state *s, int id) { return s->fld[id]; }
+
+void eko_set_poisson_dc(eko_state *s, int mode, double ghat0) { s->dc_mode = mode; s->dc_ghat0 = ghat0; }
+double eko_last_dc(eko_state *s) { return s->last_dc; }
 
 void eko_get_populations(eko_state *s, int set, double *out)
 {
@@ -625,6 +632,15 @@ void eko_fast_poisson(eko_state *s)
 
     /* cufftExecZ2Z forward, poisson.cu:86; plan main.cu:112 (NE x NY x NX) */
     fft3d(s->ext, NX, NY, NE, -1);
+
+    /* The (0,0,0) coefficient is zero by oddness in exact arithmetic; what is
+     * left is the transform's rounding residue, which the reference divides
+     * by mu := 1 (poisson.cu:176-177).  dc_mode 1 keeps that literal
+     * behaviour (with THIS transform's residue), 0 enforces zero, 2 replays a
+     * residue recorded from the reference's cuFFT run. */
+    s->last_dc = ext[0].re;
+    if (s->dc_mode == 0) { ext[0].re = 0.0; ext[0].im = 0.0; }
+    else if (s->dc_mode == 2) { ext[0].re = s->dc_ghat0; ext[0].im = 0.0; }
 
     /* gpu_derivative, poisson.cu:169-180 */
 #pragma omp parallel for collapse(2) schedule(static)

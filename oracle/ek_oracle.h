@@ -57,6 +57,10 @@ void eko_step(eko_state *s, int nsteps);           /* main.cu:189-200 */
 void eko_stream_collide_save(eko_state *s);        /* LBM.cu:465-481 */
 void eko_fast_poisson(eko_state *s);               /* poisson.cu:75-103 */
 double *eko_field(eko_state *s, int id);           /* N doubles, x fastest */
+/* DC mode of the extended right-hand side: 0 zero, 1 literal (poisson.cu:176-177,
+ * default), 2 prescribed forward coefficient ghat0 */
+void eko_set_poisson_dc(eko_state *s, int mode, double ghat0);
+double eko_last_dc(eko_state *s);
 /* populations of set 0..3 (fluid, cation, anion, temperature):
  * 27*N doubles, [d][z][y][x]; pre-collision ("X1") state */
 void eko_get_populations(eko_state *s, int set, double *out);

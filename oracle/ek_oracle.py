@@ -70,6 +70,9 @@ def lib():
         L.eko_get_populations.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
         L.eko_fft1d.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int]
         L.eko_num_threads.restype = C.c_int
+        L.eko_set_poisson_dc.argtypes = [C.c_void_p, C.c_int, C.c_double]
+        L.eko_last_dc.argtypes = [C.c_void_p]
+        L.eko_last_dc.restype = C.c_double
         _lib = L
     return _lib
 
@@ -138,6 +141,12 @@ class Oracle:
 
     def fast_poisson(self):
         self.L.eko_fast_poisson(self.h)
+
+    def set_poisson_dc(self, mode: int, ghat0: float = 0.0):
+        self.L.eko_set_poisson_dc(self.h, int(mode), float(ghat0))
+
+    def last_dc(self) -> float:
+        return self.L.eko_last_dc(self.h)
 
     def populations(self, s: int) -> np.ndarray:
         out = np.empty(27 * self.N, dtype=np.float64)

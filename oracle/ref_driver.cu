@@ -16,7 +16,12 @@
  *
  * usage: ek_ref [--steps N] [--warmup W] [--perturb AMP] [--load-init FILE]
  *               [--dump-init FILE] [--dump-final FILE] [--dump-pops FILE]
- *               [--split] [--quiet]
+ *               [--dump-dc FILE] [--split] [--quiet]
+ *
+ * --dump-dc records, per step, the (0,0,0) coefficient of the reference's own
+ * forward transform: the driver repeats extension() + cufftExecZ2Z with the
+ * reference's plan on a scratch buffer right before each fast_Poisson() call
+ * (same plan, same input: the same bits fast_Poisson sees).
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -108,7 +113,7 @@ int main(int argc, char **argv)
 {
     int steps = 0, warmup = 0, split = 0, quiet_run = 0;
     double amp = 0.0;
-    const char *load_init = NULL, *dump_init = NULL, *dump_final = NULL, *dump_p = NULL;
+    const char *load_init = NULL, *dump_init = NULL, *dump_final = NULL, *dump_p = NULL, *dump_dc = NULL;
     for (int i = 1; i < argc; ++i) {
         if (!strcmp(argv[i], "--steps") && i + 1 < argc) steps = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--warmup") && i + 1 < argc) warmup = atoi(argv[++i]);
@@ -117,6 +122,7 @@ int main(int argc, char **argv)
         else if (!strcmp(argv[i], "--dump-init") && i + 1 < argc) dump_init = argv[++i];
         else if (!strcmp(argv[i], "--dump-final") && i + 1 < argc) dump_final = argv[++i];
         else if (!strcmp(argv[i], "--dump-pops") && i + 1 < argc) dump_p = argv[++i];
+        else if (!strcmp(argv[i], "--dump-dc") && i + 1 < argc) dump_dc = argv[++i];
         else if (!strcmp(argv[i], "--split")) split = 1;
         else if (!strcmp(argv[i], "--quiet")) quiet_run = 1;
         else { fprintf(stderr, "unknown argument %s\n", argv[i]); return 2; }
@@ -189,6 +195,13 @@ int main(int argc, char **argv)
                      rho_gpu, charge_gpu, chargen_gpu, ux_gpu, uy_gpu, uz_gpu, Ex_gpu, Ey_gpu, Ez_gpu, T_gpu);
     t = 0;
 
+    cufftDoubleComplex *dc_in = NULL, *dc_out = NULL;
+    double *dc_host = NULL;
+    if (dump_dc) {
+        checkCudaErrors(cudaMalloc((void **)&dc_in, sizeof(cufftDoubleComplex) * NX * NY * NE));
+        checkCudaErrors(cudaMalloc((void **)&dc_out, sizeof(cufftDoubleComplex) * NX * NY * NE));
+        dc_host = (double *)calloc((size_t)(steps > 0 ? steps : 1), sizeof(double));
+    }
     double lbm_ms = 0.0, poi_ms = 0.0;
     float loop_ms = 0.f;
     for (int phase = 0; phase < 2; ++phase) {
@@ -204,6 +217,13 @@ int main(int argc, char **argv)
                                 temp0_gpu, temp1_gpu, temp2_gpu, rho_gpu, charge_gpu, chargen_gpu,
                                 ux_gpu, uy_gpu, uz_gpu, Ex_gpu, Ey_gpu, Ez_gpu, T_gpu, t, f0bc);
             if (split && phase == 1) cudaEventRecord(b, 0);
+            if (dump_dc && phase == 1) {
+                cufftDoubleComplex first;
+                extension(charge_gpu, chargen_gpu, dc_in);                       /* poisson.cu:83 */
+                CHECK_CUFFT(cufftExecZ2Z(plan, dc_in, dc_out, CUFFT_FORWARD));   /* poisson.cu:86 */
+                checkCudaErrors(cudaMemcpy(&first, dc_out, sizeof(first), cudaMemcpyDeviceToHost));
+                dc_host[i] = first.x;
+            }
             fast_Poisson(charge_gpu, chargen_gpu, kx, ky, kz, plan);
             if (split && phase == 1) {
                 cudaEventRecord(c, 0);
@@ -222,6 +242,11 @@ int main(int argc, char **argv)
         }
     }
 
+    if (dump_dc) {
+        FILE *f = fopen(dump_dc, "wb");
+        fwrite(dc_host, sizeof(double), steps, f);
+        fclose(f);
+    }
     if (dump_final) dump_fields(dump_final);
     if (dump_p) dump_pops(dump_p);
 

@@ -68,9 +68,10 @@ def read_pops(path: str, shape) -> np.ndarray:
 
 
 def run_ref(case: str, steps: int, perturb: float = 0.0, init_fields: dict | None = None, pops: bool = False,
-            extra=()):
+            extra=(), dc: bool = False):
     """Run the reference's own CUDA build (oracle/_ref) and return
-    (init_fields, final_fields, pops or None, info json)."""
+    (init_fields, final_fields, pops or None, info json); info["dc"] holds the
+    per-step forward DC coefficients when dc=True."""
     from oracle.build_ref import case_params
     cp = case_params(case)
     shape = (cp["NZ"], cp["NY"], cp["NX"])
@@ -85,9 +86,13 @@ def run_ref(case: str, steps: int, perturb: float = 0.0, init_fields: dict | Non
             cmd += ["--load-init", os.path.join(tmp, "load.bin")]
         if pops:
             cmd += ["--dump-pops", os.path.join(tmp, "pops.bin")]
+        if dc:
+            cmd += ["--dump-dc", os.path.join(tmp, "dc.bin")]
         cmd += list(extra)
         out = subprocess.run(cmd, check=True, capture_output=True, text=True, cwd=tmp).stdout
         info = json.loads(out.strip().splitlines()[-1])
+        if dc:
+            info["dc"] = np.fromfile(os.path.join(tmp, "dc.bin"), dtype=np.float64)
         init = read_fields(os.path.join(tmp, "init.bin"), shape)
         final = read_fields(os.path.join(tmp, "final.bin"), shape)
         p = read_pops(os.path.join(tmp, "pops.bin"), shape) if pops else None
