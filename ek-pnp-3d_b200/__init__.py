@@ -80,6 +80,7 @@ def load_library():
         getattr(L, name).argtypes = [H]
     L.ek_set_fields.argtypes = [H, C.POINTER(C.c_void_p), C.c_int]
     L.ek_step.argtypes = [H, C.c_int]
+    L.ek_step_timed.argtypes = [H, C.c_int, C.POINTER(C.c_float)]
     L.ek_stream_collide_save.argtypes = [H, C.c_int]
     L.ek_fast_poisson.argtypes = [H, C.c_int]
     L.ek_get_field.argtypes = [H, C.c_int, C.c_void_p, C.c_int]
@@ -210,6 +211,13 @@ class Simulation:
         """nsteps iterations of the loop body main.cu:189-200."""
         self._ck(self.L.ek_step(self.h, int(nsteps)), "ek_step")
         self.t += nsteps * self.p.dt
+
+    def step_timed(self, nsteps: int) -> float:
+        """step(nsteps) bracketed by CUDA events on the handle's stream; returns ms."""
+        ms = C.c_float()
+        self._ck(self.L.ek_step_timed(self.h, int(nsteps), C.byref(ms)), "ek_step_timed")
+        self.t += nsteps * self.p.dt
+        return ms.value
 
     # -- data ---------------------------------------------------------------
     def set_fields(self, fields: dict):

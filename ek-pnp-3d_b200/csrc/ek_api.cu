@@ -393,7 +393,7 @@ ek_status ek_fast_poisson(ek_handle *h, int write_efield)
         EK_CUDA(h, cudaEventRecord(e1, h->stream));
         h->ev_poi.emplace_back(e0, e1);
     }
-    h->poisson_launches += n + 2;  // + the two cuFFT executions
+    h->poisson_launches += n;      // hand-written kernels only (the two cuFFT executions are library launches)
     h->e_from_arrays = false;      // from now on E = -grad(phi) of the fresh potential
     h->efield_stale = !write_efield;
     return EK_OK;
@@ -410,6 +410,26 @@ ek_status ek_step(ek_handle *h, int nsteps)
         if (st != EK_OK) return st;
         h->steps += 1;
     }
+    return EK_OK;
+}
+
+ek_status ek_step_timed(ek_handle *h, int nsteps, float *ms)
+{
+    if (!h || !ms) return EK_ERR_INVALID;
+    DeviceGuard g(h->device);
+    cudaEvent_t e0, e1;
+    EK_CUDA(h, cudaEventCreate(&e0));
+    EK_CUDA(h, cudaEventCreate(&e1));
+    EK_CUDA(h, cudaStreamSynchronize(h->stream));
+    EK_CUDA(h, cudaEventRecord(e0, h->stream));
+    ek_status st = ek_step(h, nsteps);
+    cudaError_t e = cudaEventRecord(e1, h->stream);
+    if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (st != EK_OK) return st;
+    EK_CUDA(h, e);
     return EK_OK;
 }
 

@@ -102,6 +102,10 @@ ek_status ek_step(ek_handle *h, int nsteps);
 ek_status ek_stream_collide_save(ek_handle *h, int write_fields);
 ek_status ek_fast_poisson(ek_handle *h, int write_efield);
 
+/* ek_step bracketed by CUDA events on the handle's stream; blocks until done
+ * and returns the device time of the nsteps steps in milliseconds. */
+ek_status ek_step_timed(ek_handle *h, int nsteps, float *ms);
+
 ek_status ek_sync(ek_handle *h);
 
 /* Replaces the cudaMemcpy D2H calls of save_data_tecplot/current/record_umax

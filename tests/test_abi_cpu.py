@@ -1,0 +1,74 @@
+"""The C-ABI library loads and exports every symbol include/ek_b200.h declares
+(no compute: this runs on the CPU-only build box)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from tests import util
+
+
+def declared_functions():
+    ek = util.ek_module()
+    with open(ek.HEADER_PATH) as f:
+        text = f.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ek_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    ek = util.ek_module()
+    L = ek.load_library()
+    names = declared_functions()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in ek_b200.h but not exported by libek_b200.so"
+    assert L.ek_abi_version() == 1
+
+
+def test_params_struct_matches_the_oracle_layout():
+    ek = util.ek_module()
+    from oracle import ek_oracle as eo
+    assert [f[0] for f in ek.Params._fields_] == [f[0] for f in eo.OracleParams._fields_]
+    assert C.sizeof(ek.Params) == C.sizeof(eo.OracleParams)
+    a, b = ek.default_params(), eo.default_params()
+    for name, _ in ek.Params._fields_:
+        assert getattr(a, name) == getattr(b, name), name
+    # LBM.h as shipped
+    assert (a.NX, a.NY, a.NZ) == (50, 8, 51)
+    assert a.Lx == 50 * a.dx and a.Lz == 50 * a.dz
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product refuses to run (no silent CPU path)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    ek = util.ek_module()
+    with pytest.raises(ek.EkError):
+        ek.Simulation(ek.default_params())
+
+
+def test_invalid_arguments_are_rejected():
+    ek = util.ek_module()
+    L = ek.load_library()
+    h = C.c_void_p()
+    p = ek.default_params(NZ=3)
+    assert L.ek_create(C.byref(p), 0, C.byref(h)) == 1  # EK_ERR_INVALID before any CUDA call
+    assert L.ek_create(None, 0, C.byref(h)) == 1
+    assert L.ek_step(None, 1) == 1
+    assert L.ek_last_error(None) == b"null handle"
+
+
+def test_product_does_not_reference_the_oracle():
+    """oracle/ is test infrastructure: nothing under the package may mention it."""
+    pkg = os.path.join(util.ROOT, "ek-pnp-3d_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if "build" in dirpath.split(os.sep):
+            continue
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                with open(os.path.join(dirpath, fn)) as f:
+                    txt = f.read()
+                assert "ek_oracle" not in txt and "import oracle" not in txt and "from oracle" not in txt, fn

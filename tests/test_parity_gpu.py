@@ -1,0 +1,327 @@
+"""Parity of the CUDA path (through the C ABI) with the reference's golden
+vectors, with the CPU restatement, and -- when its binaries travelled to the
+box -- with the reference's own CUDA build run live.
+
+Tolerances are max|a-b|/max|b| per field group (components of a vector share
+the scale); see DESIGN.md "Tolerances" for why the velocity has its own."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ek_oracle as eo
+from tests import util
+from tests.test_oracle_cpu import TOL, check, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ek():
+    return util.ek_module()
+
+
+def product_run(ek, over, init, steps, mode, zchunk=None, dc=None, dc_mode=0, pops=False, every=None):
+    sim = ek.Simulation(ek.default_params(**over), stream_mode=mode, zchunk=zchunk)
+    sim.set_fields(init)
+    sim.init_equilibrium()
+    if dc is not None:
+        for n in range(steps):
+            sim.set_poisson_dc(ek.DC_PRESCRIBED, float(dc[n]))
+            sim.step(1)
+    else:
+        sim.set_poisson_dc(dc_mode)
+        sim.step(steps)
+    f = sim.fields()
+    P = np.stack([sim.populations(s) for s in range(4)]) if pops else None
+    sim.close()
+    return f, P
+
+
+def oracle_run(over, init, steps, dc_mode=0, pops=False):
+    o = eo.Oracle(eo.default_params(**over))
+    o.set_fields(init)
+    o.init_equilibrium()
+    o.set_poisson_dc(dc_mode)
+    o.step(steps)
+    f = o.fields()
+    P = np.stack([o.populations(s) for s in range(4)]) if pops else None
+    o.close()
+    return f, P
+
+
+def synthetic_init(over, amp=0.05, pb_iters=30):
+    """Reference-style start-up (shortened PB loop) plus the SURVEY 8(d) perturbation."""
+    o = eo.Oracle(eo.default_params(**dict(over, pb_iters=pb_iters)))
+    o.set_poisson_dc(0)
+    o.initialization()
+    f = eo.perturb_fields(o.fields(), amp) if amp else o.fields()
+    o.close()
+    return f
+
+
+# ---------------------------------------------------------------------------
+# against the reference's golden vectors
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("fixture", ["g1_p05_s50.npz", "g3_p05_s50.npz", "g4_p05_s50.npz"])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_matches_the_reference_golden_run(ek, fixture, mode):
+    z, meta = load_golden(fixture)
+    init = {k: z[f"init_{k}"] for k in util.FIELDS}
+    got, P = product_run(ek, meta["overrides"], init, meta["steps"], mode, dc=z["dc"], pops=True)
+    check(util.field_errors(got, {k: z[f"final_{k}"] for k in util.FIELDS}))
+    ref = z["final_fluid_pops"]
+    assert np.abs(P[0] - ref).max() <= 1e-13 * np.abs(ref).max()
+
+
+def test_startup_matches_the_reference(ek):
+    """ek_init_fields vs the reference's initialization() (501 PB iterations)."""
+    z, meta = load_golden("g4_startup.npz")
+    sim = ek.Simulation(ek.default_params(**meta["overrides"]))
+    sim.initialization()
+    got = sim.fields()
+    sim.close()
+    check(util.field_errors(got, {k: z[f"init_{k}"] for k in util.FIELDS}))
+
+
+def test_shipped_case_matches_the_reference(ek):
+    """Config C1 (50x8x51, 1000 steps, as shipped): NX is not a multiple of the
+    32-cell tile, so the masked lanes are exercised."""
+    z, meta = load_golden("c1_shipped_s1000.npz")
+    shape = (meta["overrides"]["NZ"], meta["overrides"]["NY"], meta["overrides"]["NX"])
+    init = {k: np.ascontiguousarray(np.broadcast_to(z[f"init_{k}_zprofile"][:, None, None], shape)) for k in util.FIELDS}
+    got, _ = product_run(ek, meta["overrides"], init, meta["steps"], 0, dc=z["dc"])
+    for k in ("rho", "charge", "chargen", "phi", "T", "Ez"):
+        want = z[f"final_{k}_zprofile"]
+        assert np.abs(got[k][:, 0, 0] - want).max() <= 1e-11 * np.abs(want).max(), k
+        assert np.abs(got[k] - got[k][:, :1, :1]).max() <= 1e-12 * np.abs(want).max(), k
+    want = z["final_ux_zprofile"]
+    assert np.abs(got["ux"][:, 0, 0] - want).max() <= 1e-7 * np.abs(want).max()
+
+
+# ---------------------------------------------------------------------------
+# against the CPU restatement, same DC convention on both sides
+# ---------------------------------------------------------------------------
+CASES = [
+    dict(NX=16, NY=8, NZ=13),
+    dict(NX=50, NY=3, NZ=9),                                   # ragged x tile, odd NY
+    dict(NX=33, NY=1, NZ=5),                                   # minimum NZ, NY = 1, 1-lane tail tile
+    dict(NX=24, NY=8, NZ=11, uw=1.0e-4, exf=2.0e6, voltage2=-2.5e-3),  # moving wall, body force
+    dict(NX=20, NY=6, NZ=12, TH=0.0),                          # isothermal (T == 0 exactly)
+    dict(NX=64, NY=4, NZ=10, Ext=0.0, Ra=5.0),
+]
+
+
+@pytest.mark.parametrize("over", CASES, ids=lambda o: "x".join(str(o[k]) for k in ("NX", "NY", "NZ")))
+@pytest.mark.parametrize("steps", [1, 2, 7])
+def test_matches_the_oracle(ek, over, steps):
+    init = synthetic_init(over)
+    want, wantP = oracle_run(over, init, steps, pops=True)
+    for mode in (ek.STREAM_AA, ek.STREAM_PUSH):
+        got, gotP = product_run(ek, over, init, steps, mode, pops=True)
+        err = util.field_errors(got, want)
+        if over.get("TH") == 0.0:
+            assert np.all(got["T"] == 0.0)
+        check(err)
+        for s, e in enumerate(util.pop_errors(gotP, wantP)):
+            assert e <= 1e-13, (s, e)
+
+
+def test_stream_modes_and_zchunks_are_bitwise_identical(ek):
+    over = dict(NX=40, NY=5, NZ=21)
+    init = synthetic_init(over)
+    base, baseP = product_run(ek, over, init, 5, ek.STREAM_AA, zchunk=8, pops=True)
+    for mode, zc in ((ek.STREAM_AA, 2), (ek.STREAM_AA, 5), (ek.STREAM_AA, 64), (ek.STREAM_PUSH, 3), (ek.STREAM_PUSH, 8)):
+        got, gotP = product_run(ek, over, init, 5, mode, zchunk=zc, pops=True)
+        for k in util.FIELDS:
+            assert np.array_equal(got[k], base[k]), (mode, zc, k)
+        assert np.array_equal(gotP, baseP), (mode, zc)
+
+
+def test_stage_by_stage(ek):
+    """stream_collide_save() and fast_Poisson() separately, as the reference's
+    loop calls them (main.cu:192,198)."""
+    over = dict(NX=32, NY=4, NZ=13)
+    init = synthetic_init(over)
+    o = eo.Oracle(eo.default_params(**over))
+    o.set_poisson_dc(0)
+    o.set_fields(init)
+    o.init_equilibrium()
+    sim = ek.Simulation(ek.default_params(**over))
+    sim.set_fields(init)
+    sim.init_equilibrium()
+    for it in range(3):
+        o.stream_collide_save()
+        sim.stream_collide_save(True)
+        a, b = sim.fields(), o.fields()
+        for k in ("rho", "charge", "chargen", "T"):
+            assert np.abs(a[k] - b[k]).max() <= 1e-13 * np.abs(b[k]).max(), (it, k)
+        assert np.abs(a["ux"] - b["ux"]).max() <= 1e-7 * np.abs(b["ux"]).max()
+        # phi and E are untouched by the LBM pass
+        assert np.array_equal(a["phi"], sim.field("phi"))
+        o.fast_poisson()
+        sim.fast_Poisson(True)
+        a, b = sim.fields(), o.fields()
+        for k in ("phi", "Ez"):
+            assert np.abs(a[k] - b[k]).max() <= 1e-12 * np.abs(b[k]).max(), (it, k)
+    sim.close()
+
+
+def test_literal_dc_mode_is_a_constant_interior_shift(ek):
+    over = dict(NX=20, NY=6, NZ=12)
+    init = synthetic_init(over)
+    phis = {}
+    for mode in (ek.DC_ZERO, ek.DC_LITERAL):
+        sim = ek.Simulation(ek.default_params(**over))
+        sim.set_fields(init)
+        sim.init_equilibrium()
+        sim.set_poisson_dc(mode)
+        sim.step(1)
+        phis[mode] = sim.field("phi")
+        sim.close()
+    d = (phis[ek.DC_LITERAL] - phis[ek.DC_ZERO])
+    assert np.all(d[0] == 0) and np.all(d[-1] == 0)
+    assert np.ptp(d[1:-1]) <= 1e-13 * np.abs(phis[ek.DC_ZERO]).max()
+
+
+def test_startup_matches_the_oracle(ek):
+    over = dict(NX=12, NY=4, NZ=11, pb_iters=60)
+    o = eo.Oracle(eo.default_params(**over))
+    o.set_poisson_dc(0)
+    o.initialization()
+    sim = ek.Simulation(ek.default_params(**over))
+    sim.initialization()
+    check(util.field_errors(sim.fields(), o.fields()))
+    sim.init_equilibrium()
+    o.init_equilibrium()
+    for s in range(4):
+        a, b = sim.populations(s), o.populations(s)
+        assert np.abs(a - b).max() <= 1e-14 * np.abs(b).max()
+    sim.close()
+
+
+def test_state_machine_errors(ek):
+    sim = ek.Simulation(ek.default_params(NX=8, NY=2, NZ=7))
+    with pytest.raises(ek.EkError):
+        sim.step(1)                       # before any initialisation
+    with pytest.raises(ek.EkError):
+        sim.init_equilibrium()
+    sim.set_fields({"rho": np.full(sim.shape, 1000.0)})
+    sim.init_equilibrium()
+    with pytest.raises(ek.EkError):
+        sim.set_option("stream_mode", 1)  # storage already allocated
+    with pytest.raises(ek.EkError):
+        sim.set_option("zchunk", 1)       # the owner of z=0 must own z=1
+    sim.step(2)
+    assert sim.counter("steps") == 2
+    sim.close()
+
+
+# ---------------------------------------------------------------------------
+# the reference's own CUDA build, run live (its binaries travel in oracle/_ref)
+# ---------------------------------------------------------------------------
+@pytest.mark.skipif(not util.have_ref("g2"), reason="oracle/_ref/ek_ref_g2 not built")
+def test_live_reference_without_replay(ek):
+    """NE = 32: the reference's forward cuFFT leaves an exactly zero DC
+    coefficient on this grid, so no replay is needed; 100 coupled steps."""
+    init, ref, _, info = util.run_ref("g2", 100, perturb=0.05, dc=True)
+    assert np.all(info["dc"] == 0.0)
+    got, _ = product_run(ek, util.case_overrides("g2"), init, 100, ek.STREAM_AA)
+    check(util.field_errors(got, ref))
+
+
+@pytest.mark.skipif(not util.have_ref("g3"), reason="oracle/_ref/ek_ref_g3 not built")
+def test_live_reference_with_replay_moving_wall(ek):
+    init, ref, refP, info = util.run_ref("g3", 120, perturb=0.05, pops=True, dc=True)
+    got, P = product_run(ek, util.case_overrides("g3"), init, 120, ek.STREAM_AA, dc=info["dc"], pops=True)
+    check(util.field_errors(got, ref))
+    for s, e in enumerate(util.pop_errors(P, refP)):
+        assert e <= 1e-12, (s, e)
+
+
+# ---------------------------------------------------------------------------
+# full-size, size-independent properties (config C3 256^3)
+# ---------------------------------------------------------------------------
+def test_full_size_properties(ek):
+    over = dict(NX=256, NY=256, NZ=256, pb_iters=40)
+    col = dict(NX=2, NY=2, NZ=256, pb_iters=40)
+    steps = 6
+    # (1) the un-perturbed problem is x-y uniform: the 256^3 run must equal the
+    #     oracle's 2x2x256 column to round-off, and stay uniform
+    o = eo.Oracle(eo.default_params(**col))
+    o.set_poisson_dc(0)
+    o.initialization()
+    o.init_equilibrium()
+    o.step(steps)
+    want = o.fields()
+    sim = ek.Simulation(ek.default_params(**over), stream_mode=ek.STREAM_AA)
+    sim.init()
+    m0 = None
+    sim.step(steps)
+    got = sim.fields()
+    for k in ("rho", "charge", "chargen", "phi", "T", "Ez"):
+        w = want[k][:, 0, 0]
+        assert np.abs(got[k][:, 0, 0] - w).max() <= 1e-11 * np.abs(w).max(), k
+        assert np.abs(got[k] - got[k][:, :1, :1]).max() <= 1e-11 * np.abs(w).max(), k
+    w = want["ux"][:, 0, 0]
+    assert np.abs(got["ux"][:, 0, 0] - w).max() <= 1e-6 * np.abs(w).max()
+    # (2) A-A and two-lattice push agree bit for bit at full size
+    aa_rho, aa_phi, aa_ux = got["rho"], got["phi"], got["ux"]
+    sim.close()
+    sim = ek.Simulation(ek.default_params(**over), stream_mode=ek.STREAM_PUSH)
+    sim.init()
+    sim.step(steps)
+    assert np.array_equal(sim.field("rho"), aa_rho)
+    assert np.array_equal(sim.field("phi"), aa_phi)
+    assert np.array_equal(sim.field("ux"), aa_ux)
+    # (3) fluid mass is conserved (periodic + bounce-back)
+    f = sim.populations(0)
+    mass = f.sum(dtype=np.float64)
+    assert abs(mass - 1000.0 * 256 ** 3) <= 1e-9 * 1000.0 * 256 ** 3
+    sim.close()
+
+
+# ---------------------------------------------------------------------------
+# diagnostics and dumps
+# ---------------------------------------------------------------------------
+def test_diagnostics_and_dumps(ek, tmp_path):
+    over = dict(NX=12, NY=4, NZ=9)
+    init = synthetic_init(over)
+    sim = ek.Simulation(ek.default_params(**over))
+    sim.set_fields(init)
+    sim.init_equilibrium()
+    sim.step(5)
+    f = sim.fields()
+    p = sim.p
+    # current(): LBM.cu:2674-2710
+    c = 2.0 * f["charge"][-2] - f["charge"][-3]
+    cn = 2.0 * f["chargen"][-2] - f["chargen"][-3]
+    want = ((c - cn) * f["Ez"][-1]).sum() * p.K * p.dz * p.dz
+    assert abs(sim.current() - want) <= 1e-12 * abs(want)
+    # record_umax(): LBM.cu:2712-2753
+    assert sim.max_uz() == max(0.0, float(f["uz"].max()))
+    # save_data_tecplot / save_data_end: LBM.cu:2492-2627
+    tec = tmp_path / "data.dat"
+    sim.save_data_tecplot(str(tec), time=5e-10, append=False, first=True)
+    lines = tec.read_text().splitlines()
+    assert lines[0].startswith('VARIABLES="x","y","z","u","v","w","p","charge","neg charge","phi","Ex","Ey","Ez","Temperature"')
+    assert lines[1] == ""
+    assert lines[2] == 'ZONE T="t=5e-10", F=POINT, I = 12, J = 4, K = 9'
+    assert len(lines) == 3 + 12 * 4 * 9
+    ext = {k: f[k].copy() for k in f}
+    for k in ("rho", "charge", "chargen", "ux", "uy", "uz"):
+        ext[k][0] = 2.0 * f[k][1] - f[k][2]
+        ext[k][-1] = 2.0 * f[k][-2] - f[k][-3]
+    x, y, z = 5, 2, 0
+    want_line = "%g %g %g %g %g %g %g %g %10.6f %10.6f %10.6f %10.6f %10.6f %10.6f" % (
+        p.dx * x, p.dy * y, p.dz * z, ext["ux"][z, y, x], ext["uy"][z, y, x], ext["uz"][z, y, x], ext["rho"][z, y, x],
+        ext["charge"][z, y, x], ext["chargen"][z, y, x], ext["phi"][z, y, x], ext["Ex"][z, y, x], ext["Ey"][z, y, x],
+        ext["Ez"][z, y, x], ext["T"][z, y, x])
+    assert lines[3 + (z * 4 + y) * 12 + x] == want_line
+    end = tmp_path / "data_end.dat"
+    sim.save_data_end(str(end), time=5e-10)
+    el = end.read_text().splitlines()
+    assert len(el) == 12 * 4 * 9
+    assert len(el[0].split()) == 12
+    sim.close()
