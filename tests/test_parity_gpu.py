@@ -244,8 +244,9 @@ def test_live_reference_with_replay_moving_wall(ek):
 # full-size, size-independent properties (config C3 256^3)
 # ---------------------------------------------------------------------------
 def test_full_size_properties(ek):
-    over = dict(NX=256, NY=256, NZ=256, pb_iters=40)
-    col = dict(NX=2, NY=2, NZ=256, pb_iters=40)
+    # c_inf = 0.002: with the shipped 0.01 the reference's PB start-up diverges for NZ >~ 200
+    over = dict(NX=256, NY=256, NZ=256, pb_iters=40, chargeinf=0.002)
+    col = dict(NX=2, NY=2, NZ=256, pb_iters=40, chargeinf=0.002)
     steps = 6
     # (1) the un-perturbed problem is x-y uniform: the 256^3 run must equal the
     #     oracle's 2x2x256 column to round-off, and stay uniform
