@@ -32,6 +32,10 @@ void compute_consts(const ek_params &p, EkConst &c)
     c.xhi = 0;
     c.plane = (long long)c.NY * c.PX;
     c.N = (long long)c.NZ * c.plane;
+    c.NXT = (c.PX + EK_TILE - 1) / EK_TILE;
+    c.lrow = (unsigned)c.NXT * EK_TILE_ELEMS;
+    c.lplane = (unsigned)c.NY * c.lrow;
+    c.Nlat = (unsigned long long)c.NZ * c.NY * c.NXT * EK_TILE_ELEMS;
     const double dt = p.dt, cs2 = p.cs_square;
     c.cflinv = 1.0 / p.CFL;
     c.cflinv2 = c.cflinv * c.cflinv / cs2;
@@ -115,9 +119,10 @@ ek_status ek_alloc_state(ek_handle *h)
 {
     if (h->allocated) return EK_OK;
     const size_t N = (size_t)h->c.N;
+    const size_t Nlat = (size_t)h->c.Nlat;
     const int nlat = h->stream_mode == EK_STREAM_PUSH ? 2 : 1;
     for (int l = 0; l < nlat; ++l)
-        for (int s = 0; s < 4; ++s) EK_CUDA(h, cudaMalloc((void **)&h->lat[l][s], 27 * N * sizeof(double)));
+        for (int s = 0; s < 4; ++s) EK_CUDA(h, cudaMalloc((void **)&h->lat[l][s], Nlat * sizeof(double)));
     EK_CUDA(h, cudaMalloc((void **)&h->wall, (size_t)3 * 2 * 27 * h->c.plane * sizeof(double)));
     for (int k = 0; k < EK_NFIELDS; ++k) {
         EK_CUDA(h, cudaMalloc((void **)&h->fld[k], N * sizeof(double)));
@@ -185,7 +190,9 @@ ek_status ek_create(const ek_params *p, int device, ek_handle **out)
     *out = nullptr;
     if (p->NX < 2 || p->NY < 1 || p->NZ < 5) return EK_ERR_INVALID;
     if (p->NY > 65535 || p->NZ > 65535) return EK_ERR_INVALID;
-    if ((long long)p->NX * p->NY * p->NZ >= (1LL << 31)) return EK_ERR_INVALID;  // per-slot index is 32-bit
+    if ((long long)p->NX * p->NY * p->NZ >= (1LL << 31)) return EK_ERR_INVALID;  // field index is 32-bit
+    // lattice element offsets are unsigned 32-bit (159 M cells per device)
+    if ((unsigned long long)p->NZ * p->NY * ((p->NX + 2 + 31) / 32) * EK_TILE_ELEMS >= (1ULL << 32)) return EK_ERR_INVALID;
     if (!(p->dt > 0) || !(p->CFL > 0) || !(p->cs_square > 0) || !(p->dz > 0)) return EK_ERR_INVALID;
     ek_handle *h = new (std::nothrow) ek_handle();
     if (!h) return EK_ERR_NOMEM;
@@ -236,6 +243,7 @@ ek_status ek_set_option(ek_handle *h, const char *key, long long value)
         return EK_OK;
     }
     if (!strcmp(key, "profile")) { h->profile = value != 0; return EK_OK; }
+
     return EK_ERR_INVALID;
 }
 

@@ -90,6 +90,7 @@ __global__ void k_init_equilibrium(StepArgs a, const double *r, const double *u,
     const double ux = u[i], uy = v[i], uz = w[i];
     const double Ex = ex[i], Ey = ey[i], Ez = ez[i];
     const bool wall = (z == 0 || z == c.NZ - 1);
+    const size_t li = (size_t)z * c.lplane + (size_t)y * c.lrow + ek_lat_col(x);
 #pragma unroll 1
     for (int s = 0; s < 4; ++s) {
         const double m = s == 0 ? r[i] : (s == 1 ? ch[i] : (s == 2 ? chn[i] : T[i]));
@@ -106,7 +107,7 @@ __global__ void k_init_equilibrium(StepArgs a, const double *r, const double *u,
             const double wm = c.w[ek_wclass(d)] * m;
             const double cd = cidot_literal(d, tx, ty, tz);
             const double e = d == 0 ? wm * (omusq) : wm * (omusq + cd * (1.0 + 0.5 * cd));
-            lat[(size_t)d * c.N + i] = e;
+            lat[li + (size_t)d * EK_TILE] = e;
             if (Wn) Wn[(size_t)d * c.plane] = e;
         }
     }

@@ -44,6 +44,19 @@ __host__ __device__ constexpr int ek_uwsign(int d)
 enum { EK_MODE_AA_EVEN = 0, EK_MODE_AA_ODD = 1, EK_MODE_PUSH = 2 };
 
 // ---------------------------------------------------------------------------
+// Population storage, per set: [z][y][x-tile][27 slots][32 lanes] doubles.
+// One x-tile of one row is a contiguous 6912 B block; slot d of a node is
+// 256*d bytes from slot 0 (an immediate in every load/store), and the 32 lanes
+// of a warp read one aligned 256 B segment per slot.
+// ---------------------------------------------------------------------------
+#define EK_TILE 32
+#define EK_TILE_ELEMS (27 * EK_TILE)
+__host__ __device__ inline unsigned ek_lat_col(int col)
+{
+    return (unsigned)(col >> 5) * (unsigned)EK_TILE_ELEMS + (unsigned)(col & 31);
+}
+
+// ---------------------------------------------------------------------------
 // Constants handed to every kernel by value.
 // ---------------------------------------------------------------------------
 struct EkConst {
@@ -51,7 +64,11 @@ struct EkConst {
     int PX;              // row pitch of every array (>= NX; ghost columns live in [NX, PX))
     int xlo, xhi;        // column index of the x-1 neighbour of x=0 and of the x+1 neighbour of x=NX-1
     long long plane;     // NY*PX
-    long long N;         // NZ*NY*PX : elements per direction slot / per field
+    long long N;         // NZ*NY*PX : elements per field array
+    int NXT;             // x-tiles per row of the population lattice: ceil(PX/32)
+    unsigned lrow;       // lattice elements per (z,y) row:  NXT*27*32
+    unsigned lplane;     // lattice elements per z plane:    NY*lrow
+    unsigned long long Nlat;  // lattice elements per set:   NZ*lplane  (< 2^32)
     double cflinv;       // 1/CFL                       (LBM.cu:1112)
     double cflinv2;      // cflinv*cflinv/cs_square      (LBM.cu:1115)
     double inv_cs2;      // 1/cs_square
@@ -73,7 +90,7 @@ struct EkConst {
 
 struct StepArgs {
     EkConst c;
-    double *in[4];        // population lattices, [27][N] per set
+    double *in[4];        // population lattices (tiled layout above), Nlat doubles per set
     double *out[4];       // == in for the A-A scheme
     double *wall;         // scalar-set wall state: [3 sets][2 planes][27][plane]
     const double *phi;    // potential (E = -grad phi fused into the step)

@@ -36,22 +36,38 @@ struct Sh {
     double u[3][32];
 };
 
-// element offsets of the 3x3x3 neighbourhood of a node inside one slot
+// Offsets of the 3x3x3 neighbourhood of a node.  Populations live in a tiled
+// layout per set, [z][y][x-tile][27 slots][32 lanes] (ek_internal.cuh): the slot
+// stride is a compile-time 256 B, so the 27 accesses of a node differ only by an
+// immediate and one 64-bit address per neighbour position is all the integer
+// work a gather or scatter needs.  Macroscopic fields stay in the reference's
+// [z][y][x] order (LBM.cu:22-25).
 struct Nbr {
-    int xo[3];  // column of x-1, x, x+1
-    int yo[3];  // row offset (y-1, y, y+1)*PX
-    int zo[3];  // plane offset (z-1, z, z+1)*plane, z periodic
-    __device__ __forceinline__ int at(int ax, int ay, int az) const { return zo[az + 1] + yo[ay + 1] + xo[ax + 1]; }
-    __device__ __forceinline__ int c() const { return zo[1] + yo[1] + xo[1]; }
+    unsigned lx[3], ly[3], lz[3];  // lattice element offsets of x-1,x,x+1 / y-1,y,y+1 / z-1,z,z+1 (z periodic)
+    int fx[3], fy[3], fz[3];       // the same for the field arrays
+    __device__ __forceinline__ unsigned at(int ax, int ay, int az) const { return lz[az + 1] + ly[ay + 1] + lx[ax + 1]; }
+    __device__ __forceinline__ unsigned lc() const { return lz[1] + ly[1] + lx[1]; }
+    __device__ __forceinline__ int fc() const { return fz[1] + fy[1] + fx[1]; }
 };
+
+__device__ __forceinline__ void set_xy(Nbr &nb, const EkConst &c, int x, int y)
+{
+    nb.fx[0] = x == 0 ? c.xlo : x - 1;
+    nb.fx[1] = x;
+    nb.fx[2] = x == c.NX - 1 ? c.xhi : x + 1;
+    const int ym = y == 0 ? c.NY - 1 : y - 1, yp = y == c.NY - 1 ? 0 : y + 1;
+    nb.fy[0] = ym * c.PX; nb.fy[1] = y * c.PX; nb.fy[2] = yp * c.PX;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) nb.lx[k] = ek_lat_col(nb.fx[k]);
+    nb.ly[0] = (unsigned)ym * c.lrow; nb.ly[1] = (unsigned)y * c.lrow; nb.ly[2] = (unsigned)yp * c.lrow;
+}
 
 __device__ __forceinline__ void set_z(Nbr &nb, const EkConst &c, int z)
 {
     const int zm = z == 0 ? c.NZ - 1 : z - 1;
     const int zp = z == c.NZ - 1 ? 0 : z + 1;
-    nb.zo[0] = (int)(zm * c.plane);
-    nb.zo[1] = (int)(z * c.plane);
-    nb.zo[2] = (int)(zp * c.plane);
+    nb.fz[0] = (int)(zm * c.plane); nb.fz[1] = (int)(z * c.plane); nb.fz[2] = (int)(zp * c.plane);
+    nb.lz[0] = (unsigned)zm * c.lplane; nb.lz[1] = (unsigned)z * c.lplane; nb.lz[2] = (unsigned)zp * c.lplane;
 }
 
 __device__ __forceinline__ void bar_moments() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
@@ -59,25 +75,32 @@ __device__ __forceinline__ void bar_velocity() { asm volatile("bar.sync 2, 128;"
 
 // pre-collision populations of a node ("pull" restatement)
 template <int MODE>
-__device__ __forceinline__ void gather27(const double *lat, long long N, const Nbr &nb, double S[27])
+__device__ __forceinline__ void gather27(const double *lat, const Nbr &nb, double S[27])
 {
+    if (MODE == EK_MODE_AA_ODD) {
 #pragma unroll
-    for (int d = 0; d < 27; ++d) {
-        if (MODE == EK_MODE_AA_ODD)
-            S[d] = lat[(size_t)ek_opp(d) * N + nb.at(-ek_cx(d), -ek_cy(d), -ek_cz(d))];
-        else
-            S[d] = lat[(size_t)d * N + nb.c()];
+        for (int d = 0; d < 27; ++d) {
+            const double *q = lat + nb.at(-ek_cx(d), -ek_cy(d), -ek_cz(d));
+            S[d] = q[ek_opp(d) * EK_TILE];
+        }
+    } else {
+        const double *q = lat + nb.lc();
+#pragma unroll
+        for (int d = 0; d < 27; ++d) S[d] = q[d * EK_TILE];
     }
 }
 
 // where the post-collision population of direction d goes
 template <int MODE, int d>
-__device__ __forceinline__ void put(double *lat, long long N, const Nbr &nb, double v)
+__device__ __forceinline__ void put(double *lat, const Nbr &nb, double v)
 {
-    if (MODE == EK_MODE_AA_EVEN)
-        lat[(size_t)ek_opp(d) * N + nb.c()] = v;
-    else
-        lat[(size_t)d * N + nb.at(ek_cx(d), ek_cy(d), ek_cz(d))] = v;
+    if (MODE == EK_MODE_AA_EVEN) {
+        double *q = lat + nb.lc();
+        q[ek_opp(d) * EK_TILE] = v;
+    } else {
+        double *q = lat + nb.at(ek_cx(d), ek_cy(d), ek_cz(d));
+        q[d * EK_TILE] = v;
+    }
 }
 
 // LBM.cu:621-630: left-to-right sum in index order
@@ -119,15 +142,15 @@ __device__ __forceinline__ void efield_at(const StepArgs &a, const Nbr &nb, int 
 {
     const EkConst &c = a.c;
     if (EARR) {
-        const int i = nb.c();
+        const int i = nb.fc();
         E[0] = a.E[0][i]; E[1] = a.E[1][i]; E[2] = a.E[2][i];
     } else {
         const double *phi = a.phi;
-        const int zb = nb.zo[1];
-        E[0] = 0.5 * (phi[zb + nb.yo[1] + nb.xo[0]] - phi[zb + nb.yo[1] + nb.xo[2]]) / c.dx;
-        E[1] = 0.5 * (phi[zb + nb.yo[0] + nb.xo[1]] - phi[zb + nb.yo[2] + nb.xo[1]]) / c.dy;
+        const int zb = nb.fz[1];
+        E[0] = 0.5 * (phi[zb + nb.fy[1] + nb.fx[0]] - phi[zb + nb.fy[1] + nb.fx[2]]) / c.dx;
+        E[1] = 0.5 * (phi[zb + nb.fy[0] + nb.fx[1]] - phi[zb + nb.fy[2] + nb.fx[1]]) / c.dy;
         const int zc = z < 1 ? 1 : (z > c.NZ - 2 ? c.NZ - 2 : z);
-        const int col = nb.yo[1] + nb.xo[1];
+        const int col = nb.fy[1] + nb.fx[1];
         E[2] = 0.5 * (phi[(size_t)(zc - 1) * c.plane + col] - phi[(size_t)(zc + 1) * c.plane + col]) / c.dz;
     }
 }
@@ -157,20 +180,20 @@ struct ScalarPairs {
         if (act) {
             if (!wall) {
                 if (MODE == EK_MODE_AA_EVEN) {
-                    put<MODE, d>(lout, c.N, nb, Oa);
-                    put<MODE, o>(lout, c.N, nb, Ob);
+                    put<MODE, d>(lout, nb, Oa);
+                    put<MODE, o>(lout, nb, Ob);
                 } else {
                     // inflow into wall nodes is discarded (LBM.cu:2102-2218 overwrite it)
                     const int za = z + ek_cz(d), zb = z - ek_cz(d);
-                    if (ek_cz(d) == 0 || !(za == 0 || za == c.NZ - 1)) put<MODE, d>(lout, c.N, nb, Oa);
-                    if (ek_cz(d) == 0 || !(zb == 0 || zb == c.NZ - 1)) put<MODE, o>(lout, c.N, nb, Ob);
+                    if (ek_cz(d) == 0 || !(za == 0 || za == c.NZ - 1)) put<MODE, d>(lout, nb, Oa);
+                    if (ek_cz(d) == 0 || !(zb == 0 || zb == c.NZ - 1)) put<MODE, o>(lout, nb, Ob);
                 }
             } else {
                 // the wall feeds the first interior plane ...
                 if (ek_cz(d) != 0) {
                     const bool a_inward = bottom ? (ek_cz(d) > 0) : (ek_cz(d) < 0);
-                    if (a_inward) put<MODE, d>(lout, c.N, nb, Oa);
-                    else put<MODE, o>(lout, c.N, nb, Ob);
+                    if (a_inward) put<MODE, d>(lout, nb, Oa);
+                    else put<MODE, o>(lout, nb, Ob);
                 }
                 // ... and itself: ions swap post-collision populations
                 // (LBM.cu:2132-2218), temperature anti-bounce-back (LBM.cu:2226-2413)
@@ -214,7 +237,7 @@ __device__ __forceinline__ void scalar_role(const StepArgs &a, Sh &sh, const int
     if (z0 == 0) {
         // the bottom wall needs the moments of the z = 1 node first (LBM.cu:663-801)
         set_z(nb, c, 1);
-        gather27<MODE>(lin, c.N, nb, S);
+        gather27<MODE>(lin, nb, S);
         mom_sh[lane] = sum27(S);
         if (is_temp) {
             double E[3];
@@ -234,7 +257,7 @@ __device__ __forceinline__ void scalar_role(const StepArgs &a, Sh &sh, const int
 #pragma unroll
             for (int d = 0; d < 27; ++d) S[d] = Wn[(size_t)d * c.plane];
         } else {
-            gather27<MODE>(lin, c.N, nb, S);
+            gather27<MODE>(lin, nb, S);
         }
         const double m = sum27(S);
         double E[3] = {0.0, 0.0, 0.0};
@@ -243,7 +266,7 @@ __device__ __forceinline__ void scalar_role(const StepArgs &a, Sh &sh, const int
             efield_at<EARR>(a, nb, z, E);
             sh.E[0][lane] = E[0]; sh.E[1][lane] = E[1]; sh.E[2][lane] = E[2];
         }
-        if (FULL && act) a.fld[3 + s][nb.c()] = m;  // charge, chargen, T (LBM.cu:811-813)
+        if (FULL && act) a.fld[3 + s][nb.fc()] = m;  // charge, chargen, T (LBM.cu:811-813)
         bar_moments();
         // E is read between the two barriers: the temperature warp may only
         // overwrite it after every warp has passed bar_velocity()
@@ -262,7 +285,7 @@ __device__ __forceinline__ void scalar_role(const StepArgs &a, Sh &sh, const int
         // rest population: relaxed in place (LBM.cu:1712-1714); wall rule LBM.cu:2131,2231,2385
         const double O0 = S[0] - wp * (S[0] - wcm[0] * omusq);
         if (act) {
-            if (!wall) lout[nb.c()] = O0;
+            if (!wall) lout[nb.lc()] = O0;
             else if (!is_temp) Wn[0] = O0;
             else if (bottom) Wn[0] = -O0 + c.twoTw[0];
             else Wn[0] = -O0;
@@ -309,8 +332,8 @@ struct FluidPairs {
             }
         }
         if (act) {
-            put<MODE, d>(lout, c.N, nb, Oa);
-            put<MODE, o>(lout, c.N, nb, Ob);
+            put<MODE, d>(lout, nb, Oa);
+            put<MODE, o>(lout, nb, Ob);
         }
         FluidPairs<MODE, p + 1>::run(S, wcr, omusq, u, F, uF, wall, top, c, lout, nb, act);
     }
@@ -346,7 +369,7 @@ __device__ __forceinline__ void fluid_role(const StepArgs &a, Sh &sh, const int 
 
     if (z0 == 0) {
         set_z(nb, c, 1);
-        gather27<MODE>(lin, c.N, nb, S);
+        gather27<MODE>(lin, nb, S);
         double m[3];
         momentum(S, m);
         bar_moments();
@@ -360,7 +383,7 @@ __device__ __forceinline__ void fluid_role(const StepArgs &a, Sh &sh, const int 
         set_z(nb, c, z);
         const bool top = (z == c.NZ - 1);
         const bool wall = (z == 0) || top;
-        gather27<MODE>(lin, c.N, nb, S);
+        gather27<MODE>(lin, nb, S);
         const double rho = sum27(S);
         double m[3];
         momentum(S, m);
@@ -379,7 +402,7 @@ __device__ __forceinline__ void fluid_role(const StepArgs &a, Sh &sh, const int 
         sh.u[0][lane] = u[0]; sh.u[1][lane] = u[1]; sh.u[2][lane] = u[2];
         bar_velocity();
         if (act) {
-            const int i = nb.c();
+            const int i = nb.fc();
             a.dq[i] = dq;
             if (FULL) {  // LBM.cu:807-810
                 a.fld[0][i] = rho; a.fld[1][i] = u[0]; a.fld[2][i] = u[1]; a.fld[3][i] = u[2];
@@ -393,8 +416,8 @@ __device__ __forceinline__ void fluid_role(const StepArgs &a, Sh &sh, const int 
         double O0 = S[0];
         if (!wall) O0 = S[0] - c.wp[0] * (S[0] - wcr[0] * omusq) + c.dt * (c.sp * (-c.coe[0] * uF));
         if (act) {
-            if (MODE == EK_MODE_PUSH) lout[nb.c()] = O0;
-            else if (!wall) lout[nb.c()] = O0;
+            if (MODE == EK_MODE_PUSH) lout[nb.lc()] = O0;
+            else if (!wall) lout[nb.lc()] = O0;
         }
         FluidPairs<MODE, 0>::run(S, wcr, omusq, u, F, uF, wall, top, c, lout, nb, act);
     }
@@ -414,12 +437,7 @@ __global__ void __launch_bounds__(128, 4) ek_step_kernel(const __grid_constant__
     const int z0 = blockIdx.z * a.zchunk;
     const int z1 = min(z0 + a.zchunk, c.NZ);
     Nbr nb;
-    nb.xo[0] = x == 0 ? c.xlo : x - 1;
-    nb.xo[1] = x;
-    nb.xo[2] = x == c.NX - 1 ? c.xhi : x + 1;
-    nb.yo[0] = (y == 0 ? c.NY - 1 : y - 1) * c.PX;
-    nb.yo[1] = y * c.PX;
-    nb.yo[2] = (y == c.NY - 1 ? 0 : y + 1) * c.PX;
+    set_xy(nb, c, x, y);
     const int pi = y * c.PX + x;
     if (role == 0) fluid_role<MODE, FULL>(a, sh, lane, act, nb, z0, z1);
     else scalar_role<MODE, FULL, EARR>(a, sh, role, lane, act, nb, pi, z0, z1);
@@ -434,12 +452,7 @@ __global__ void ek_export_kernel(const StepArgs a, int s, double *dst)
     if (x >= c.NX) return;
     const int y = blockIdx.y, z = blockIdx.z;
     Nbr nb;
-    nb.xo[0] = x == 0 ? c.xlo : x - 1;
-    nb.xo[1] = x;
-    nb.xo[2] = x == c.NX - 1 ? c.xhi : x + 1;
-    nb.yo[0] = (y == 0 ? c.NY - 1 : y - 1) * c.PX;
-    nb.yo[1] = y * c.PX;
-    nb.yo[2] = (y == c.NY - 1 ? 0 : y + 1) * c.PX;
+    set_xy(nb, c, x, y);
     set_z(nb, c, z);
     double S[27];
     const bool wall = (z == 0 || z == c.NZ - 1);
@@ -448,7 +461,7 @@ __global__ void ek_export_kernel(const StepArgs a, int s, double *dst)
 #pragma unroll
         for (int d = 0; d < 27; ++d) S[d] = Wn[(size_t)d * c.plane];
     } else {
-        gather27<MODE>(a.in[s], c.N, nb, S);
+        gather27<MODE>(a.in[s], nb, S);
     }
     const size_t cells = (size_t)c.NX * c.NY * c.NZ;
     const size_t o = (size_t)c.NX * ((size_t)c.NY * z + y) + x;
