@@ -243,6 +243,11 @@ ek_status ek_set_option(ek_handle *h, const char *key, long long value)
         return EK_OK;
     }
     if (!strcmp(key, "profile")) { h->profile = value != 0; return EK_OK; }
+    if (!strcmp(key, "poisson_path")) {
+        if (value != 0 && value != 1) return EK_ERR_INVALID;
+        h->poisson_path = (int)value;
+        return EK_OK;
+    }
 
     return EK_ERR_INVALID;
 }
@@ -306,8 +311,8 @@ ek_status ek_init_fields(ek_handle *h)
         // E is only observable after the last solve (it is taken from the un-relaxed phi)
         const bool last = (i == h->p.pb_iters - 1);
         int n = 0;
-        st = ek_poisson_solve(h, h->poisson, c, h->dq, h->fld[EK_PHI], last ? h->fld[EK_EX] : nullptr,
-                              h->fld[EK_EY], h->fld[EK_EZ], h->dc_mode, h->dc_ghat0, h->stream, &n);  // LBM.cu:96
+        st = ek_poisson_solve(h, h->poisson, h->p, c, h->dq, h->fld[EK_PHI], last ? h->fld[EK_EX] : nullptr,
+                              h->fld[EK_EY], h->fld[EK_EZ], h->poisson_path, h->dc_mode, h->dc_ghat0, h->stream, &n);  // LBM.cu:96
         if (st != EK_OK) return st;
         ek_launch_pbe_relax(c, h->p.PB_omega, h->fld[EK_PHI], h->phi_old, h->stream);  // LBM.cu:98-104
     }
@@ -394,8 +399,8 @@ ek_status ek_fast_poisson(ek_handle *h, int write_efield)
         EK_CUDA(h, cudaEventRecord(e0, h->stream));
     }
     int n = 0;
-    ek_status st = ek_poisson_solve(h, h->poisson, h->c, h->dq, h->fld[EK_PHI], write_efield ? h->fld[EK_EX] : nullptr,
-                                    h->fld[EK_EY], h->fld[EK_EZ], h->dc_mode, h->dc_ghat0, h->stream, &n);
+    ek_status st = ek_poisson_solve(h, h->poisson, h->p, h->c, h->dq, h->fld[EK_PHI], write_efield ? h->fld[EK_EX] : nullptr,
+                                    h->fld[EK_EY], h->fld[EK_EZ], h->poisson_path, h->dc_mode, h->dc_ghat0, h->stream, &n);
     if (st != EK_OK) return st;
     if (h->profile) {
         EK_CUDA(h, cudaEventRecord(e1, h->stream));

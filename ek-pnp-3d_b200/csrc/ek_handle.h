@@ -33,6 +33,7 @@ struct ek_handle {
     bool efield_stale = false;     // Ex/Ey/Ez arrays are older than phi (recomputed on demand)
     int zchunk = 8;
     int dc_mode = EK_DC_ZERO;
+    int poisson_path = 0;          // 0: xy-FFT + tridiagonal z-solve, 1: odd-extension 3-D FFT
     double dc_ghat0 = 0.0;
 
     // counters / profiling

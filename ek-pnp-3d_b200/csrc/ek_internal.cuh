@@ -134,16 +134,19 @@ struct EkPoisson {
     double *real_ext = nullptr;          // [NE][NY][NX]
     cufftDoubleComplex *spec = nullptr;  // [NE][NY][NXH]
     double *kx2 = nullptr, *ky2 = nullptr, *kz_term = nullptr;  // device tables
-    void *work = nullptr;
-    size_t work_bytes = 0;
+    // path 0: batched 2-D transforms + tridiagonal z-solve
+    cufftHandle plan2_fwd = 0, plan2_inv = 0;
+    bool plans2 = false;
+    cufftDoubleComplex *spec2 = nullptr;  // [NZ-2][NY][NXH]
+    double *cp = nullptr;                 // LU factor c'_j of every column, [NZ-2][NY*NXH]
 };
 
 ek_status ek_poisson_create(ek_handle *h, EkPoisson &P, const ek_params &p, int PX, cudaStream_t st);
 void ek_poisson_destroy(EkPoisson &P);
 // dq = c+ - c-  ->  phi (and Ex,Ey,Ez when E != nullptr)
-ek_status ek_poisson_solve(ek_handle *h, EkPoisson &P, const EkConst &c, const double *dq, double *phi,
-                           double *Ex, double *Ey, double *Ez, int dc_mode, double dc_ghat0, cudaStream_t st,
-                           int *launches);
+ek_status ek_poisson_solve(ek_handle *h, EkPoisson &P, const ek_params &p, const EkConst &c, const double *dq,
+                           double *phi, double *Ex, double *Ey, double *Ez, int path, int dc_mode, double dc_ghat0,
+                           cudaStream_t st, int *launches);
 void ek_launch_efield(const EkConst &c, const double *phi, double *Ex, double *Ey, double *Ez, cudaStream_t st);
 
 // ---------------------------------------------------------------------------

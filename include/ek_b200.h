@@ -133,7 +133,9 @@ ek_status ek_get_populations(ek_handle *h, int set, double *dst, int dst_on_devi
 ek_status ek_set_poisson_dc(ek_handle *h, int mode, double ghat0);
 
 /* options: "stream_mode" (EK_STREAM_*; before ek_init*), "zchunk",
- * "profile" (1: time every LBM/Poisson launch with CUDA events). */
+ * "poisson_path" (0: 2-D FFT + tridiagonal z-solve, default; 1: the
+ * reference's odd-extension 3-D FFT), "profile" (1: time every LBM/Poisson
+ * launch with CUDA events). */
 ek_status ek_set_option(ek_handle *h, const char *key, long long value);
 /* counters: "steps", "lbm_launches", "poisson_launches", "kernel_launches";
  * times (ms, profile on): "lbm_ms", "poisson_ms" */

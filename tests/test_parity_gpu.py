@@ -326,3 +326,56 @@ def test_diagnostics_and_dumps(ek, tmp_path):
     assert len(el) == 12 * 4 * 9
     assert len(el[0].split()) == 12
     sim.close()
+
+
+# ---------------------------------------------------------------------------
+# the two realisations of the Poisson stage (ek_poisson.cu)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("over", [dict(NX=16, NY=8, NZ=13), dict(NX=50, NY=6, NZ=33),
+                                  dict(NX=8, NY=4, NZ=256, chargeinf=0.002),
+                                  dict(NX=12, NY=5, NZ=64, voltage2=-1.0e-3)],
+                         ids=lambda o: "x".join(str(o[k]) for k in ("NX", "NY", "NZ")))
+def test_poisson_paths_agree(ek, over):
+    """path 0 (2-D FFT + tridiagonal z-solve) against path 1 (the reference's
+    odd-extension FFT) and against the oracle, on the same c+ - c-."""
+    init = synthetic_init(over, pb_iters=40)
+    o = eo.Oracle(eo.default_params(**over))
+    o.set_poisson_dc(0)
+    o.set_fields(init)
+    o.fast_poisson()
+    want = o.fields()
+    got = {}
+    for path in (0, 1):
+        sim = ek.Simulation(ek.default_params(**over))
+        sim.set_option("poisson_path", path)
+        sim.set_fields(init)
+        sim.init_equilibrium()
+        sim.fast_Poisson(True)
+        got[path] = sim.fields()
+        sim.close()
+        for k in ("phi", "Ex", "Ey", "Ez"):
+            scale = max(np.abs(want[n]).max() for n in (("phi",) if k == "phi" else ("Ex", "Ey", "Ez")))
+            assert np.abs(got[path][k] - want[k]).max() <= 1e-12 * scale, (path, k)
+        assert np.all(got[path]["phi"][0] == sim.p.voltage) and np.all(got[path]["phi"][-1] == sim.p.voltage2)
+    assert np.abs(got[0]["phi"] - got[1]["phi"]).max() <= 1e-12 * np.abs(want["phi"]).max()
+
+
+def test_prescribed_dc_is_the_same_shift_on_both_paths(ek):
+    over = dict(NX=16, NY=4, NZ=12)
+    init = synthetic_init(over)
+    res = {}
+    for path in (0, 1):
+        sim = ek.Simulation(ek.default_params(**over))
+        sim.set_option("poisson_path", path)
+        sim.set_fields(init)
+        sim.init_equilibrium()
+        sim.set_poisson_dc(ek.DC_PRESCRIBED, 0.37)
+        sim.fast_Poisson(True)
+        res[path] = sim.field("phi")
+        sim.set_poisson_dc(ek.DC_ZERO)
+        sim.fast_Poisson(True)
+        base = sim.field("phi")
+        size = 16 * 4 * 2 * 11
+        assert np.abs((res[path] - base)[1:-1] + 0.37 / size).max() < 1e-16
+        sim.close()
+    assert np.abs(res[0] - res[1]).max() <= 1e-13 * np.abs(res[1]).max()
