@@ -27,7 +27,7 @@ void compute_consts(const ek_params &p, EkConst &c)
 {
     memset(&c, 0, sizeof(c));
     c.NX = p.NX; c.NY = p.NY; c.NZ = p.NZ;
-    c.PX = p.NX;
+    c.PX = (p.NX + 1) & ~1;  // even row pitch: every z-plane of a field array stays 16 B aligned for cuFFT
     c.xlo = p.NX - 1;
     c.xhi = 0;
     c.plane = (long long)c.NY * c.PX;
