@@ -208,7 +208,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, help="c1|c2|c3|c4 (default c3 at N=1, c4 at N>1)")
     ap.add_argument("--stream-mode", default="aa", choices=["aa", "push"])
-    ap.add_argument("--zchunk", type=int, default=8)
+    ap.add_argument("--zchunk", type=int, default=32)
     ap.add_argument("--ref-all", action="store_true", help="reference arm: try every nThreads variant")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

@@ -82,7 +82,11 @@ void free_state(ek_handle *h)
     for (int l = 0; l < 2; ++l)
         for (int s = 0; s < 4; ++s) { cudaFree(h->lat[l][s]); h->lat[l][s] = nullptr; }
     cudaFree(h->wall); h->wall = nullptr;
-    for (int k = 0; k < EK_NFIELDS; ++k) { cudaFree(h->fld[k]); h->fld[k] = nullptr; }
+    for (int k = 0; k < EK_NFIELDS; ++k) {
+        if (!h->fld_external[k]) cudaFree(h->fld[k]);
+        h->fld[k] = nullptr;
+        h->fld_external[k] = false;
+    }
     cudaFree(h->dq); h->dq = nullptr;
     cudaFree(h->phi_old); h->phi_old = nullptr;
     ek_poisson_destroy(h->poisson);
@@ -443,6 +447,43 @@ ek_status ek_step_timed(ek_handle *h, int nsteps, float *ms)
     cudaEventDestroy(e1);
     if (st != EK_OK) return st;
     EK_CUDA(h, e);
+    return EK_OK;
+}
+
+ek_status ek_adopt_field(ek_handle *h, int id, double *dev_ptr)
+{
+    if (!h || !dev_ptr || id < 0 || id >= EK_NFIELDS) return EK_ERR_INVALID;
+    if (h->c.PX != h->c.NX) { ek_set_error(h, "ek_adopt_field needs an even NX (dense rows)"); return EK_ERR_INVALID; }
+    if (h->allocated && h->fld[id] == dev_ptr) return EK_OK;
+    DeviceGuard g(h->device);
+    ek_status st = ek_alloc_state(h);
+    if (st != EK_OK) return st;
+    EK_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (!h->fld_external[id]) cudaFree(h->fld[id]);
+    h->fld[id] = dev_ptr;
+    h->fld_external[id] = true;
+    return EK_OK;
+}
+
+ek_status ek_refresh_charge_difference(ek_handle *h)
+{
+    if (!h) return EK_ERR_INVALID;
+    if (!h->allocated) return EK_ERR_STATE;
+    DeviceGuard g(h->device);
+    dim3 b(128), gr((h->c.NX + 127) / 128, h->c.NY, h->c.NZ);
+    k_dq_from_fields<<<gr, b, 0, h->stream>>>(h->c, h->fld[EK_CHARGE], h->fld[EK_CHARGEN], h->dq);
+    EK_CUDA(h, cudaGetLastError());
+    return EK_OK;
+}
+
+ek_status ek_mark_fields_ready(ek_handle *h)
+{
+    if (!h) return EK_ERR_INVALID;
+    if (!h->allocated) return EK_ERR_STATE;
+    h->fields_ready = true;
+    h->pops_ready = false;
+    h->e_from_arrays = true;
+    h->efield_stale = false;
     return EK_OK;
 }
 

@@ -22,6 +22,7 @@ struct ek_handle {
     int parity = 0;         // AA: 0 natural layout, 1 after an even step
     double *wall = nullptr; // scalar-set wall state
     double *fld[EK_NFIELDS] = {};
+    bool fld_external[EK_NFIELDS] = {};  // adopted caller arrays (ek_adopt_field): not freed by the handle
     double *dq = nullptr;
     double *phi_old = nullptr;
     EkPoisson poisson;
@@ -31,7 +32,7 @@ struct ek_handle {
     bool pops_ready = false;       // populations initialised
     bool e_from_arrays = false;    // next LBM pass takes E from the arrays, not from grad(phi)
     bool efield_stale = false;     // Ex/Ey/Ez arrays are older than phi (recomputed on demand)
-    int zchunk = 8;
+    int zchunk = 32;
     int dc_mode = EK_DC_ZERO;
     int poisson_path = 0;          // 0: xy-FFT + tridiagonal z-solve, 1: odd-extension 3-D FFT
     double dc_ghat0 = 0.0;

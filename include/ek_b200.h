@@ -113,6 +113,16 @@ ek_status ek_sync(ek_handle *h);
 ek_status ek_get_field(ek_handle *h, int id, double *dst, int dst_on_device);
 /* Device pointer of a macroscopic array (owned by the handle). */
 ek_status ek_field_ptr(ek_handle *h, int id, double **dev_ptr);
+/* Make the handle use a caller-owned device array (reference layout, NX even)
+ * as its macroscopic array `id` -- what the reference's main() allocates at
+ * main.cu:94-106.  The handle never frees it.  ek_mark_fields_ready() declares
+ * that the adopted arrays now hold an initial state written by the caller
+ * (e.g. by the reference's own initialization(), LBM.cu:68). */
+ek_status ek_adopt_field(ek_handle *h, int id, double *dev_ptr);
+ek_status ek_mark_fields_ready(ek_handle *h);
+/* Recompute c+ - c- from the charge/chargen arrays (after a caller wrote them,
+ * e.g. the reference's gpu_PBE, LBM.cu:139-146) before ek_fast_poisson. */
+ek_status ek_refresh_charge_difference(ek_handle *h);
 /* Pre-collision populations of one set in the reference's layout:
  * 27*N doubles, [d][z][y][x], d = 0 the rest population (f0|f1 of
  * LBM.cu:17-30 back to back).  For tests. */

@@ -379,3 +379,45 @@ def test_prescribed_dc_is_the_same_shift_on_both_paths(ek):
         assert np.abs((res[path] - base)[1:-1] + 0.37 / size).max() < 1e-16
         sim.close()
     assert np.abs(res[0] - res[1]).max() <= 1e-13 * np.abs(res[1]).max()
+
+
+# ---------------------------------------------------------------------------
+# the reference-signature shim (libek_b200_shim.so)
+# ---------------------------------------------------------------------------
+def test_reference_signature_shim(ek):
+    """Drive the library exactly as the reference's main() drives its own code:
+    caller-owned device arrays, init_equilibrium(18 ptrs), then
+    stream_collide_save(24 args) + fast_Poisson(6 args) per step."""
+    import ctypes as C
+    import subprocess
+    import torch
+    so = os.path.join(os.path.dirname(ek.LIB_PATH), "libek_b200_shim.so")
+    syms = subprocess.run(["nm", "-D", so], capture_output=True, text=True, check=True).stdout.split()
+    mangled = {n: next(s for s in syms if s.startswith("_Z") and n in s) for n in
+               ("init_equilibrium", "stream_collide_save", "fast_Poisson")}
+    L = C.CDLL(so)
+    over = dict(NX=32, NY=4, NZ=13)
+    init = synthetic_init(over)
+    p = ek.default_params(**over)
+    L.ek_shim_configure(C.byref(p))
+    dev = torch.device("cuda", 0)
+    arr = {k: torch.from_numpy(np.ascontiguousarray(init[k])).to(dev) for k in util.FIELDS}
+    ptr = {k: C.c_void_p(v.data_ptr()) for k, v in arr.items()}
+    scratch = torch.zeros(8, dtype=torch.float64, device=dev)  # stands in for the caller's population arrays
+    sp = C.c_void_p(scratch.data_ptr())
+    L.ek_shim_bind_potential(ptr["phi"], ptr["Ex"], ptr["Ey"], ptr["Ez"])
+    getattr(L, mangled["init_equilibrium"])(sp, sp, sp, sp, sp, sp, sp, sp, ptr["rho"], ptr["charge"], ptr["chargen"],
+                                            ptr["ux"], ptr["uy"], ptr["uz"], ptr["Ex"], ptr["Ey"], ptr["Ez"], ptr["T"])
+    scs = getattr(L, mangled["stream_collide_save"])
+    scs.argtypes = [C.c_void_p] * 22 + [C.c_double, C.c_void_p]
+    fp = getattr(L, mangled["fast_Poisson"])
+    fp.argtypes = [C.c_void_p] * 5 + [C.c_int]
+    steps = 5
+    for _ in range(steps):
+        scs(sp, sp, sp, sp, sp, sp, sp, sp, sp, sp, sp, sp, ptr["rho"], ptr["charge"], ptr["chargen"], ptr["ux"],
+            ptr["uy"], ptr["uz"], ptr["Ex"], ptr["Ey"], ptr["Ez"], ptr["T"], 0.0, sp)
+        fp(ptr["charge"], ptr["chargen"], sp, sp, sp, 0)
+    torch.cuda.synchronize()
+    got = {k: v.cpu().numpy() for k, v in arr.items()}
+    want, _ = oracle_run(over, init, steps)
+    check(util.field_errors(got, want))
