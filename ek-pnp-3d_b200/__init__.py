@@ -93,6 +93,22 @@ def load_library():
     L.ek_stream.restype = C.c_void_p
     L.ek_last_error.argtypes = [H]
     L.ek_last_error.restype = C.c_char_p
+    # multi-GPU slabs
+    L.ek_create_slab.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.c_int, C.POINTER(H)]
+    L.ek_set_stream.argtypes = [H, C.c_void_p]
+    L.ek_halo_doubles.argtypes = [H]
+    L.ek_halo_doubles.restype = C.c_longlong
+    L.ek_halo_pack.argtypes = [H, C.c_int, C.c_void_p, C.c_void_p]
+    L.ek_halo_unpack.argtypes = [H, C.c_int, C.c_void_p, C.c_void_p]
+    L.ek_phi_halo_pack.argtypes = [H, C.c_void_p, C.c_void_p]
+    L.ek_phi_halo_unpack.argtypes = [H, C.c_void_p, C.c_void_p]
+    L.ek_dq_ptr.argtypes = [H, C.POINTER(C.c_void_p)]
+    L.ek_zsolve_columns.argtypes = [H, C.c_void_p, C.c_int, C.c_int]
+    L.ek_poisson_finish.argtypes = [H, C.c_int]
+    for name in ("ek_compute_efield", "ek_init_uniform", "ek_pbe", "ek_pbe_relax", "ek_ensure_allocated",
+                 "ek_mark_fields_ready", "ek_refresh_charge_difference", "ek_row_pitch", "ek_lbm_parity"):
+        getattr(L, name).argtypes = [H]
+    L.ek_adopt_field.argtypes = [H, C.c_int, C.c_void_p]
     L.ek_wall_current.argtypes = [H, C.POINTER(C.c_double)]
     L.ek_max_uz.argtypes = [H, C.POINTER(C.c_double)]
     L.ek_save_data_tecplot.argtypes = [H, C.c_char_p, C.c_double, C.c_int, C.c_int]
@@ -122,11 +138,22 @@ class Simulation:
     """One coupled EK-PNP simulation on one CUDA device."""
 
     def __init__(self, params: Params | None = None, device: int = -1, stream_mode: int | None = None,
-                 zchunk: int | None = None, profile: bool = False):
+                 zchunk: int | None = None, profile: bool = False, slab: tuple | None = None):
+        """slab=(rank, nranks): this handle owns the x-slab `rank` of the global
+        domain described by `params` (multi-GPU path, see slab.py)."""
         self.L = load_library()
         self.p = params if params is not None else default_params()
         self.h = C.c_void_p()
-        st = self.L.ek_create(C.byref(self.p), int(device), C.byref(self.h))
+        self.device = int(device)
+        if slab is None:
+            st = self.L.ek_create(C.byref(self.p), int(device), C.byref(self.h))
+        else:
+            rank, nranks = slab
+            self.global_params = self.p
+            st = self.L.ek_create_slab(C.byref(self.p), int(device), int(rank), int(nranks), C.byref(self.h))
+            local = Params.from_buffer_copy(self.p)
+            local.NX = self.p.NX // int(nranks)
+            self.p = local
         if st != 0:
             self.h = C.c_void_p()
             raise EkError(f"ek_create failed: {_STATUS.get(st, st)} (is a CUDA device present? there is no CPU path)")

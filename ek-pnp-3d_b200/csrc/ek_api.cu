@@ -22,14 +22,23 @@ __global__ void k_dq_from_fields(EkConst c, const double *ch, const double *chn,
     dq[i] = ch[i] - chn[i];
 }
 
+}  // namespace
+
 // derived constants, each evaluated in the form the reference uses
-void compute_consts(const ek_params &p, EkConst &c)
+void ek_compute_consts(const ek_params &p, EkConst &c, bool slab)
 {
     memset(&c, 0, sizeof(c));
     c.NX = p.NX; c.NY = p.NY; c.NZ = p.NZ;
-    c.PX = (p.NX + 1) & ~1;  // even row pitch: every z-plane of a field array stays 16 B aligned for cuFFT
-    c.xlo = p.NX - 1;
-    c.xhi = 0;
+    if (!slab) {
+        c.PX = (p.NX + 1) & ~1;  // even row pitch: every z-plane of a field array stays 16 B aligned for cuFFT
+        c.xlo = p.NX - 1;        // periodic wrap inside the array
+        c.xhi = 0;
+    } else {
+        // x-slab of a larger domain: two ghost columns after the NX owned ones
+        c.PX = (p.NX + 2 + 1) & ~1;
+        c.xhi = p.NX;            // column holding the right neighbour's x = 0
+        c.xlo = p.NX + 1;        // column holding the left neighbour's last x
+    }
     c.plane = (long long)c.NY * c.PX;
     c.N = (long long)c.NZ * c.plane;
     c.NXT = (c.PX + EK_TILE - 1) / EK_TILE;
@@ -77,6 +86,8 @@ void compute_consts(const ek_params &p, EkConst &c)
     c.voltage = p.voltage; c.voltage2 = p.voltage2;
 }
 
+namespace {
+
 void free_state(ek_handle *h)
 {
     for (int l = 0; l < 2; ++l)
@@ -89,15 +100,10 @@ void free_state(ek_handle *h)
     }
     cudaFree(h->dq); h->dq = nullptr;
     cudaFree(h->phi_old); h->phi_old = nullptr;
+    cudaFree(h->cp_cols); h->cp_cols = nullptr; h->cp_ky0 = -1; h->cp_kyl = 0;
     ek_poisson_destroy(h->poisson);
     h->allocated = false;
 }
-
-struct DeviceGuard {
-    int prev = -1;
-    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (dev != prev) cudaSetDevice(dev); }
-    ~DeviceGuard() { int cur; cudaGetDevice(&cur); if (cur != prev && prev >= 0) cudaSetDevice(prev); }
-};
 
 void collect_events(ek_handle *h)
 {
@@ -201,7 +207,7 @@ ek_status ek_create(const ek_params *p, int device, ek_handle **out)
     ek_handle *h = new (std::nothrow) ek_handle();
     if (!h) return EK_ERR_NOMEM;
     h->p = *p;
-    compute_consts(*p, h->c);
+    ek_compute_consts(*p, h->c, false);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -224,7 +230,7 @@ ek_status ek_destroy(ek_handle *h)
     cudaStreamSynchronize(h->stream);
     collect_events(h);
     free_state(h);
-    cudaStreamDestroy(h->stream);
+    if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
     return EK_OK;
 }
@@ -396,6 +402,10 @@ ek_status ek_fast_poisson(ek_handle *h, int write_efield)
 {
     if (!h) return EK_ERR_INVALID;
     if (!h->allocated) { ek_set_error(h, "ek_fast_poisson before initialisation"); return EK_ERR_STATE; }
+    if (h->nranks > 1) {
+        ek_set_error(h, "x-slab of a multi-rank domain: the distributed solve is driven by the host (slab.py)");
+        return EK_ERR_STATE;
+    }
     DeviceGuard g(h->device);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->profile) {

@@ -7,11 +7,23 @@
 
 #include "ek_internal.cuh"
 
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (dev != prev) cudaSetDevice(dev); }
+    ~DeviceGuard() { int cur; cudaGetDevice(&cur); if (cur != prev && prev >= 0) cudaSetDevice(prev); }
+};
+
 struct ek_handle {
-    ek_params p;
+    ek_params p;          // local parameters: NX is the slab width, Lx the GLOBAL length
     EkConst c;
     int device = 0;
     cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    // x-slab decomposition (ek_slab.cu): rank r owns global columns [r*NX, (r+1)*NX)
+    int rank = 0, nranks = 1, NXg = 0;
+    bool slab = false;
+    double *cp_cols = nullptr;     // LU factor for the distributed z-solve (cached)
+    int cp_ky0 = -1, cp_kyl = 0;
     std::string err;
 
     // storage
@@ -44,5 +56,6 @@ struct ek_handle {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_lbm, ev_poi;
 };
 
+void ek_compute_consts(const ek_params &p, EkConst &c, bool slab);
 ek_status ek_alloc_state(ek_handle *h);
 StepArgs ek_step_args(ek_handle *h);

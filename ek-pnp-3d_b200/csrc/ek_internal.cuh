@@ -148,6 +148,11 @@ ek_status ek_poisson_solve(ek_handle *h, EkPoisson &P, const ek_params &p, const
                            double *phi, double *Ex, double *Ey, double *Ez, int path, int dc_mode, double dc_ghat0,
                            cudaStream_t st, int *launches);
 void ek_launch_efield(const EkConst &c, const double *phi, double *Ex, double *Ey, double *Ez, cudaStream_t st);
+void ek_launch_zfactor_cols(int ncols, int NXg, int NY, int ky0, int M, double Lx, double Ly, double dz, double *cp,
+                            cudaStream_t st);
+void ek_launch_zsolve(int nreal, int ncols, int M, double *x, const double *cp, double scale_dz2, double lift0,
+                      double lift1, double norm, double dc_offset, int lift_r, cudaStream_t st);
+void ek_launch_set_walls(const EkConst &c, double *phi, cudaStream_t st);
 
 // ---------------------------------------------------------------------------
 // LBM stage (ek_lbm.cu) and start-up kernels (ek_init.cu)

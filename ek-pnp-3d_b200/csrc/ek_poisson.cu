@@ -117,12 +117,12 @@ __global__ void k_zfactor(int ncols, int NXH, int M, const double *__restrict__ 
 template <int UNROLL>
 __global__ void __launch_bounds__(128) k_zsolve(int nreal, int ncols, int M, double *__restrict__ x,
                                                 const double *__restrict__ cp, double scale_dz2, double lift0,
-                                                double lift1, double norm, double dc_offset)
+                                                double lift1, double norm, double dc_offset, int lift_r)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nreal) return;
     const int col = r >> 1;
-    const bool lifted = (r == 0);  // real part of the (kx,ky) = (0,0) column
+    const bool lifted = (r == lift_r);  // real part of the (kx,ky) = (0,0) column (-1: not in this set of columns)
     double prev = 0.0;
     int j = 0;
     // forward elimination; loads are independent of the recurrence, so a block
@@ -244,6 +244,44 @@ ek_status create_path0(ek_handle *h, EkPoisson &P, const ek_params &p, cudaStrea
 
 }  // namespace
 
+// LU factor for an arbitrary block of columns of the FULL (complex-to-complex
+// in x) spectrum: column = iky*NXg + ikx, ky index ky0+iky, used by the
+// distributed solve (ek_slab.cu)
+__global__ void k_zfactor_cols(int ncols, int NXg, int NY, int ky0, int M, double Lx, double Ly, double dz,
+                               double *__restrict__ cp)
+{
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= ncols) return;
+    const int ikx = col % NXg, iky = ky0 + col / NXg;
+    // wavenumbers in FFT order (main.cu:119-145)
+    const double I = (ikx <= NXg / 2 ? (double)ikx : (double)ikx - NXg) * 2.0 * M_PI / Lx;
+    const double J = (iky <= NY / 2 ? (double)iky : (double)iky - NY) * 2.0 * M_PI / Ly;
+    const double b = -(2.0 + (I * I + J * J) * dz * dz);
+    double cprev = 0.0;
+    for (int j = 0; j < M; ++j) {
+        cprev = 1.0 / (b - cprev);
+        cp[(size_t)j * ncols + col] = cprev;
+    }
+}
+
+void ek_launch_zfactor_cols(int ncols, int NXg, int NY, int ky0, int M, double Lx, double Ly, double dz, double *cp,
+                            cudaStream_t st)
+{
+    k_zfactor_cols<<<(ncols + 127) / 128, 128, 0, st>>>(ncols, NXg, NY, ky0, M, Lx, Ly, dz, cp);
+}
+
+void ek_launch_zsolve(int nreal, int ncols, int M, double *x, const double *cp, double scale_dz2, double lift0,
+                      double lift1, double norm, double dc_offset, int lift_r, cudaStream_t st)
+{
+    k_zsolve<8><<<(nreal + 127) / 128, 128, 0, st>>>(nreal, ncols, M, x, cp, scale_dz2, lift0, lift1, norm, dc_offset,
+                                                       lift_r);
+}
+
+void ek_launch_set_walls(const EkConst &c, double *phi, cudaStream_t st)
+{
+    k_set_walls<<<dim3((c.NX + 127) / 128, c.NY), 128, 0, st>>>(c, phi);
+}
+
 void ek_launch_efield(const EkConst &c, const double *phi, double *Ex, double *Ey, double *Ez, cudaStream_t st)
 {
     dim3 b(128), g((c.NX + 127) / 128, c.NY, c.NZ);
@@ -301,7 +339,7 @@ ek_status ek_poisson_solve(ek_handle *h, EkPoisson &P, const ek_params &p, const
         const double off = dc_mode == EK_DC_PRESCRIBED ? -dc_ghat0 / size : 0.0;
         k_zsolve<8><<<(nreal + 127) / 128, 128, 0, st>>>(nreal, ncols, M, reinterpret_cast<double *>(P.spec2), P.cp,
                                                            -(c.CtoC / c.eps) * c.dz * c.dz, -c.voltage * nxy,
-                                                           -c.voltage2 * nxy, 1.0 / nxy, off);
+                                                           -c.voltage2 * nxy, 1.0 / nxy, off, 0);
         EK_CUFFT(h, cufftExecZ2D(P.plan2_inv, P.spec2, phi + c.plane));
         k_set_walls<<<dim3((c.NX + 127) / 128, c.NY), b, 0, st>>>(c, phi);
         n = 2;

@@ -168,6 +168,40 @@ ek_status ek_max_uz(ek_handle *h, double *umax);
 ek_status ek_save_data_tecplot(ek_handle *h, const char *path, double time, int append, int first);
 ek_status ek_save_data_end(ek_handle *h, const char *path, double time);
 
+/* ------------------------------------------------------------------------
+ * Multi-GPU: x-slab decomposition (new; the reference is single-GPU,
+ * main.cu:58).  One handle per slab/process/GPU; the host moves the buffers
+ * between ranks (ek-pnp-3d_b200/slab.py over torch.distributed/NCCL).
+ * `global` describes the whole domain; rank r owns columns
+ * [r*NX/nranks, (r+1)*NX/nranks).  Slabs use the A-A scheme.
+ * ------------------------------------------------------------------------ */
+ek_status ek_create_slab(const ek_params *global, int device, int rank, int nranks, ek_handle **out);
+/* run on a caller-provided cudaStream_t (e.g. torch's current stream) */
+ek_status ek_set_stream(ek_handle *h, void *stream);
+ek_status ek_ensure_allocated(ek_handle *h);
+int ek_row_pitch(ek_handle *h);          /* doubles per row of a field array (>= NX, ghosts included) */
+int ek_lbm_parity(ek_handle *h);         /* 1 after an even (local) A-A step, 0 after an odd one */
+/* population halos: 4 sets x 9 populations x NY x NZ doubles per face.
+ * phase 0: after an even step (boundary columns -> neighbours' ghost columns),
+ * phase 1: after an odd step (ghost columns -> neighbours' boundary columns). */
+long long ek_halo_doubles(ek_handle *h);
+ek_status ek_halo_pack(ek_handle *h, int phase, double *to_left, double *to_right);
+ek_status ek_halo_unpack(ek_handle *h, int phase, const double *from_left, const double *from_right);
+/* one ghost column of phi per face (NY x NZ doubles) for the fused E = -grad(phi) */
+ek_status ek_phi_halo_pack(ek_handle *h, double *to_left, double *to_right);
+ek_status ek_phi_halo_unpack(ek_handle *h, const double *from_left, const double *from_right);
+/* distributed Poisson stage: c+ - c- array, the z-solve on a block of ky rows
+ * of the full-x spectrum [NZ-2][kyl][NXglobal] complex, and the epilogue
+ * (wall planes of phi, flags) once the host has written phi's interior */
+ek_status ek_dq_ptr(ek_handle *h, double **dev_ptr);
+ek_status ek_zsolve_columns(ek_handle *h, double *spec, int ky0, int kyl);
+ek_status ek_poisson_finish(ek_handle *h, int write_efield);
+ek_status ek_compute_efield(ek_handle *h);
+/* the pieces of initialization() (LBM.cu:68-146) for a host-driven PB loop */
+ek_status ek_init_uniform(ek_handle *h);
+ek_status ek_pbe(ek_handle *h);
+ek_status ek_pbe_relax(ek_handle *h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,132 @@
+"""Host-side logic of the multi-GPU path on CPU: partitioning, the transports
+(torch.distributed with gloo, world_size 2) and the transposes of the
+distributed Poisson stage, with the device z-solve replaced by a dense solve.
+The result is checked against the oracle's fast_Poisson."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import ek_oracle as eo
+from tests import util
+
+
+def slab_mod():
+    import importlib
+    util.ek_module()
+    return importlib.import_module("ek-pnp-3d_b200.slab")
+
+
+def test_partition_and_ky_chunks():
+    slab = slab_mod()
+    assert slab.partition(1024, 8)[3] == (384, 512)
+    with pytest.raises(ValueError):
+        slab.partition(50, 4)
+    nyh, kyl = slab.ky_chunks(256, 8)
+    assert (nyh, kyl) == (129, 17) and kyl * 8 >= nyh
+    assert slab.ky_chunks(8, 2) == (5, 3)
+
+
+def zsolve_dense(X, p, ky0, NXg, NY):
+    """what ek_zsolve_columns does, as dense solves (numpy, tiny grids only)"""
+    M, kyl, _ = X.shape
+    out = np.zeros_like(X)
+    nxy = NXg * NY
+    for iy in range(kyl):
+        ky = ky0 + iy
+        J = (ky if ky <= NY // 2 else ky - NY) * 2 * np.pi / p.Ly
+        for ix in range(NXg):
+            I = (ix if ix <= NXg // 2 else ix - NXg) * 2 * np.pi / p.Lx
+            A = (np.diag(np.full(M, -(2.0 + (I * I + J * J) * p.dz ** 2))) + np.diag(np.ones(M - 1), 1)
+                 + np.diag(np.ones(M - 1), -1))
+            d = -(p.convertCtoCharge / p.eps) * p.dz ** 2 * X[:, iy, ix]
+            if ky == 0 and ix == 0:
+                d = d.copy()
+                d[0] += -p.voltage * nxy
+                d[-1] += -p.voltage2 * nxy
+            out[:, iy, ix] = np.linalg.solve(A, d) / nxy
+    return out
+
+
+def run_distributed_poisson(slab, comm, p, dq_local, ranks):
+    """dq_local: {rank: (NZ, NY, NXl)} -> {rank: phi interior (M, NY, NXl)}"""
+    P = comm.nranks
+    nyh, kyl = slab.ky_chunks(p.NY, P)
+    send = [slab.y_forward(torch.from_numpy(dq_local[r][1:-1].copy()), P, kyl) for r in ranks]
+    recv = comm.all_to_all(send)
+    back = []
+    for r, rc in zip(ranks, recv):
+        X = slab.x_forward(rc)
+        X = torch.from_numpy(zsolve_dense(X.numpy(), p, r * kyl, p.NX, p.NY))
+        back.append(slab.x_backward(X, P))
+    recv = comm.all_to_all(back)
+    return {r: slab.y_backward(rc, p.NY).numpy() for r, rc in zip(ranks, recv)}
+
+
+def oracle_case():
+    p = eo.default_params(NX=12, NY=6, NZ=8, voltage2=-2.0e-3)
+    o = eo.Oracle(p)
+    o.set_poisson_dc(0)
+    rng = np.random.default_rng(3)
+    f = o.fields()
+    f["charge"] = 0.01 * (1 + 0.1 * rng.standard_normal(o.shape))
+    f["chargen"] = 0.01 * (1 + 0.1 * rng.standard_normal(o.shape))
+    o.set_fields(f)
+    o.fast_poisson()
+    return p, f["charge"] - f["chargen"], o.field("phi").copy()
+
+
+@pytest.mark.parametrize("P", [1, 2, 3, 4])
+def test_local_transport_matches_the_oracle(P):
+    slab = slab_mod()
+    p, dq, phi = oracle_case()
+    parts = slab.partition(p.NX, P)
+    comm = slab.LocalComm(P)
+    got = run_distributed_poisson(slab, comm, p, {r: dq[:, :, a:b] for r, (a, b) in enumerate(parts)}, list(range(P)))
+    full = np.concatenate([got[r] for r in range(P)], axis=2)
+    assert np.abs(full - phi[1:-1]).max() <= 1e-12 * np.abs(phi).max()
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        slab = slab_mod()
+        comm = slab.DistComm(dist)
+        # ring exchange: what my neighbours sent must arrive on the right side
+        to_l, to_r = torch.full((4,), 10.0 * rank + 1), torch.full((4,), 10.0 * rank + 2)
+        fl, fr = torch.zeros(4), torch.zeros(4)
+        comm.neighbor_exchange([to_l], [to_r], [fl], [fr])
+        left, right = (rank - 1) % world, (rank + 1) % world
+        ok = bool((fl == 10.0 * left + 2).all() and (fr == 10.0 * right + 1).all())
+        p, dq, phi = oracle_case()
+        a, b = slab.partition(p.NX, world)[rank]
+        got = run_distributed_poisson(slab, comm, p, {rank: dq[:, :, a:b]}, [rank])[rank]
+        err = float(np.abs(got - phi[1:-1, :, a:b]).max() / np.abs(phi).max())
+        m = comm.max_over_ranks(float(rank))
+        q.put((rank, ok, err, m))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world_size_2():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    for rank, ok, err, m in res:
+        assert ok, f"rank {rank}: neighbour exchange delivered the wrong buffers"
+        assert err <= 1e-12, (rank, err)
+        assert m == 1.0

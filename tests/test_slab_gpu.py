@@ -1,0 +1,85 @@
+"""The multi-slab algorithm (halo phases A/B, phi halos, distributed Poisson,
+host-driven start-up) checked on ONE GPU: all slabs of the group live in this
+process and the collectives are copies (slab.LocalComm).  Reference = the
+single-domain run of the same library and the oracle."""
+import importlib
+
+import numpy as np
+import pytest
+
+from oracle import ek_oracle as eo
+from tests import util
+from tests.test_oracle_cpu import check
+from tests.test_parity_gpu import oracle_run, product_run, synthetic_init
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ek():
+    return util.ek_module()
+
+
+@pytest.fixture(scope="module")
+def slab(ek):
+    return importlib.import_module("ek-pnp-3d_b200.slab")
+
+
+@pytest.mark.parametrize("P", [1, 2, 4])
+@pytest.mark.parametrize("steps", [1, 2, 5])
+def test_slabs_match_the_single_domain_run(ek, slab, P, steps):
+    over = dict(NX=64, NY=6, NZ=13)
+    init = synthetic_init(over)
+    want, wantP = product_run(ek, over, init, steps, ek.STREAM_AA, pops=True)
+    grp = slab.SlabGroup(ek, ek.default_params(**over), slab.LocalComm(P))
+    grp.set_fields(init)
+    grp.init_equilibrium()
+    grp.step(steps)
+    got = grp.gather_fields()
+    check(util.field_errors(got, want))
+    for s in range(4):
+        a = grp.gather_populations(s)
+        assert np.abs(a - wantP[s]).max() <= 1e-13 * np.abs(wantP[s]).max(), s
+    grp.close()
+
+
+def test_slabs_match_the_oracle_with_walls_moving(ek, slab):
+    over = dict(NX=48, NY=4, NZ=11, uw=1.0e-4, exf=2.0e6, voltage2=-2.5e-3)
+    init = synthetic_init(over)
+    want, _ = oracle_run(over, init, 6)
+    grp = slab.SlabGroup(ek, ek.default_params(**over), slab.LocalComm(3))
+    grp.set_fields(init)
+    grp.init_equilibrium()
+    grp.step(3)
+    grp.step(3)
+    check(util.field_errors(grp.gather_fields(), want))
+    grp.close()
+
+
+def test_slab_startup_matches_the_single_domain_startup(ek, slab):
+    over = dict(NX=32, NY=4, NZ=11, pb_iters=40)
+    sim = ek.Simulation(ek.default_params(**over))
+    sim.initialization()
+    want = sim.fields()
+    sim.close()
+    grp = slab.SlabGroup(ek, ek.default_params(**over), slab.LocalComm(2))
+    grp.initialization()
+    check(util.field_errors(grp.gather_fields(), want))
+    grp.init_equilibrium()
+    grp.step(2)
+    o = eo.Oracle(eo.default_params(**over))
+    o.set_poisson_dc(0)
+    o.initialization()
+    o.init_equilibrium()
+    o.step(2)
+    check(util.field_errors(grp.gather_fields(), o.fields()))
+    grp.close()
+
+
+def test_single_handle_refuses_the_distributed_solve(ek):
+    sim = ek.Simulation(ek.default_params(NX=32, NY=2, NZ=7), slab=(0, 2))
+    sim.set_fields({"rho": np.full(sim.shape, 1000.0)})
+    sim.init_equilibrium()
+    with pytest.raises(ek.EkError):
+        sim.fast_Poisson()
+    sim.close()
