@@ -219,6 +219,24 @@ class SlabGroup:
         self.nranks = comm.nranks
         self.slabs = [Slab(ek, params, r, self.nranks, device, zchunk) for r in comm.local_ranks]
         self.t = 0.0
+        self.profile = False          # per-phase CUDA-event timing (development aid)
+        self._ev = []
+
+    def _mark(self, name):
+        if self.profile:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self._ev.append((name, e))
+
+    def phase_times(self) -> dict:
+        """ms per phase accumulated since the last call (profile=True)"""
+        torch.cuda.synchronize()
+        out = {}
+        for (n0, e0), (n1, e1) in zip(self._ev[:-1], self._ev[1:]):
+            if n1 != "begin":
+                out[n1] = out.get(n1, 0.0) + e0.elapsed_time(e1)
+        self._ev = []
+        return out
 
     def close(self):
         for s in self.slabs:
@@ -243,11 +261,19 @@ class SlabGroup:
 
     def poisson(self):
         """the distributed fast_Poisson(): dq -> phi (interior, walls, ghost columns)"""
-        recv = self.comm.all_to_all([s.poisson_forward_local() for s in self.slabs])
-        recv = self.comm.all_to_all([s.poisson_middle(r) for s, r in zip(self.slabs, recv)])
+        send = [s.poisson_forward_local() for s in self.slabs]
+        self._mark("poisson_y_fft_pack")
+        recv = self.comm.all_to_all(send)
+        self._mark("poisson_all_to_all_1")
+        send = [s.poisson_middle(r) for s, r in zip(self.slabs, recv)]
+        self._mark("poisson_x_fft_zsolve")
+        recv = self.comm.all_to_all(send)
+        self._mark("poisson_all_to_all_2")
         for s, r in zip(self.slabs, recv):
             s.poisson_backward_local(r)
+        self._mark("poisson_unpack_y_ifft")
         self.phi_halo_exchange()
+        self._mark("phi_halo")
 
     # -- the reference's call sequence ---------------------------------------------
     def initialization(self):
@@ -287,9 +313,12 @@ class SlabGroup:
         for i in range(nsteps):
             full = i == nsteps - 1
             parity = self.slabs[0].L.ek_lbm_parity(self.slabs[0].h)
+            self._mark("begin")
             for s in self.slabs:
                 s.sim.stream_collide_save(full)
+            self._mark("lbm")
             self.halo_exchange(0 if parity == 0 else 1)
+            self._mark("population_halo")
             self.poisson()
             if full:
                 for s in self.slabs:
@@ -345,6 +374,9 @@ def bench_slabs(ek, dist, args, w, wl, local_rank):
     mlups = cells * args.steps / (ms * 1e-3) / 1e6
     peak, peak_src = measured_peak()
     launches = sum(int(s.sim.counter("kernel_launches")) for s in grp.slabs)
+    grp.profile = True
+    grp.step(max(4, args.warmup))
+    phases = {k: round(v / max(4, args.warmup), 4) for k, v in grp.phase_times().items()}
     grp.close()
     step_gbs = mlups * 1e6 * B_ALG_STEP / 1e9
     return {"metric": "coupled_step_mlups", "value": round(mlups, 2), "unit": "MLUPS", "n_gpus": comm.nranks,
@@ -353,7 +385,7 @@ def bench_slabs(ek, dist, args, w, wl, local_rank):
             "config": {"workload": w["name"], "grid": [NX, NY, NZ], "stream_mode": "aa", "zchunk": args.zchunk,
                        "parallelism": f"x-slabs x{comm.nranks}: NCCL halo send/recv + all-to-all Poisson transposes",
                        "cells_per_gpu": cells // comm.nranks, "init": "reference start-up (PB iterations) %.2f s" % init_s,
-                       "l2": "per-GPU working set >> 126 MB L2"},
+                       "l2": "per-GPU working set >> 126 MB L2", "phase_ms_rank0": phases},
             "roofline": {"bound": "hbm", "achieved": round(step_gbs / comm.nranks, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(step_gbs / comm.nranks / peak, 4), "peak_source": peak_src,
                          "note": "whole coupled step per GPU at 1760 B/cell (kernel split is reported at N=1)",
