@@ -100,16 +100,24 @@ class LocalComm:
     def __init__(self, nranks: int):
         self.nranks = nranks
         self.local_ranks = list(range(nranks))
+        _blocking(self)
 
-    def neighbor_exchange(self, to_left, to_right, from_left, from_right):
+    def neighbor_exchange_start(self, to_left, to_right, from_left, from_right):
         P = self.nranks
         for r in range(P):
             from_left[r].copy_(to_right[(r - 1) % P])
             from_right[r].copy_(to_left[(r + 1) % P])
+        return None
 
-    def all_to_all(self, send):
+    def neighbor_exchange_finish(self, handle):
+        pass
+
+    def all_to_all_start(self, send):
         P = self.nranks
         return [torch.stack([send[p][r] for p in range(P)]) for r in range(P)]
+
+    def all_to_all_finish(self, handle):
+        return handle
 
     def barrier(self):
         torch.cuda.synchronize()
@@ -126,27 +134,38 @@ class DistComm:
         self.rank = dist.get_rank()
         self.nranks = dist.get_world_size()
         self.local_ranks = [self.rank]
+        _blocking(self)
 
-    def neighbor_exchange(self, to_left, to_right, from_left, from_right):
+    def neighbor_exchange_start(self, to_left, to_right, from_left, from_right):
+        """post the ring send/recv; the transfer runs on NCCL's stream while the
+        caller keeps launching kernels, until neighbor_exchange_finish()"""
         d, P, r = self.dist, self.nranks, self.rank
         left, right = (r - 1) % P, (r + 1) % P
         if P == 1:
             from_left[0].copy_(to_right[0])
             from_right[0].copy_(to_left[0])
-            return
+            return []
         # order matters when left == right (P = 2): the peer's first send (its
         # to_right) is my from_left, its second (to_left) my from_right
         ops = [d.P2POp(d.isend, to_right[0], right), d.P2POp(d.isend, to_left[0], left),
                d.P2POp(d.irecv, from_left[0], left), d.P2POp(d.irecv, from_right[0], right)]
-        for req in d.batch_isend_irecv(ops):
+        return d.batch_isend_irecv(ops)
+
+    def neighbor_exchange_finish(self, handle):
+        for req in handle:
             req.wait()
 
-    def all_to_all(self, send):
+    def all_to_all_start(self, send):
         recv = torch.empty_like(send[0])
         if self.nranks == 1:
             recv.copy_(send[0])
-        else:
-            self.dist.all_to_all_single(recv, send[0])
+            return (None, recv)
+        return (self.dist.all_to_all_single(recv, send[0], async_op=True), recv)
+
+    def all_to_all_finish(self, handle):
+        work, recv = handle
+        if work is not None:
+            work.wait()
         return [recv]
 
     def barrier(self):
@@ -158,6 +177,18 @@ class DistComm:
         t = torch.tensor([x], dtype=torch.float64, device="cuda" if torch.cuda.is_available() else "cpu")
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
+
+
+def _blocking(comm):
+    """blocking forms, shared by both transports"""
+    def neighbor_exchange(to_left, to_right, from_left, from_right):
+        comm.neighbor_exchange_finish(comm.neighbor_exchange_start(to_left, to_right, from_left, from_right))
+
+    def all_to_all(send):
+        return comm.all_to_all_finish(comm.all_to_all_start(send))
+    comm.neighbor_exchange = neighbor_exchange
+    comm.all_to_all = all_to_all
+    return comm
 
 
 # ---------------------------------------------------------------------------
@@ -193,9 +224,10 @@ class Slab:
         self.sim._ck(st, what)
 
     # -- Poisson pieces --------------------------------------------------------
-    def poisson_forward_local(self) -> torch.Tensor:
-        """real FFT along y of the interior planes, split by ky chunk: (P, M, kyl, NX) complex"""
-        return y_forward(self.dq[1:-1, :, :self.NX], self.nranks, self.kyl)
+    def poisson_forward_local(self, z0: int = 0, z1: int | None = None) -> torch.Tensor:
+        """real FFT along y of interior planes [z0, z1), split by ky chunk: (P, z1-z0, kyl, NX) complex"""
+        z1 = self.M if z1 is None else z1
+        return y_forward(self.dq[1 + z0:1 + z1, :, :self.NX], self.nranks, self.kyl)
 
     def poisson_middle(self, recv: torch.Tensor) -> torch.Tensor:
         """recv (P, M, kyl, NXl): my ky chunk, every rank's x block -> x FFT, z-solve, back"""
@@ -204,10 +236,16 @@ class Slab:
                 "ek_zsolve_columns")
         return x_backward(X, self.nranks)
 
-    def poisson_backward_local(self, recv: torch.Tensor):
-        """recv (P, M, kyl, NX): every ky chunk of my x block -> inverse real FFT along y -> phi"""
-        self.phi[1:-1, :, :self.NX] = y_backward(recv, self.NY)
-        self.ck(self.L.ek_poisson_finish(self.h, 0), "ek_poisson_finish")
+    def poisson_backward_local(self, recv: torch.Tensor, z0: int = 0, z1: int | None = None, last: bool = True):
+        """recv (P, z1-z0, kyl, NX): every ky chunk of my x block -> inverse real FFT along y -> phi"""
+        z1 = self.M if z1 is None else z1
+        self.phi[1 + z0:1 + z1, :, :self.NX] = y_backward(recv, self.NY)
+        if last:
+            self.ck(self.L.ek_poisson_finish(self.h, 0), "ek_poisson_finish")
+
+    def zsolve(self, X: torch.Tensor):
+        self.ck(self.L.ek_zsolve_columns(self.h, C.c_void_p(X.data_ptr()), self.rank * self.kyl, self.kyl),
+                "ek_zsolve_columns")
 
 
 # ---------------------------------------------------------------------------
@@ -219,6 +257,7 @@ class SlabGroup:
         self.nranks = comm.nranks
         self.slabs = [Slab(ek, params, r, self.nranks, device, zchunk) for r in comm.local_ranks]
         self.t = 0.0
+        self.zchunks = 4              # pipeline depth of the Poisson transposes
         self.profile = False          # per-phase CUDA-event timing (development aid)
         self._ev = []
 
@@ -243,13 +282,19 @@ class SlabGroup:
             s.sim.close()
 
     # -- exchanges ---------------------------------------------------------------
-    def halo_exchange(self, phase: int):
+    def halo_exchange_start(self, phase: int):
         for s in self.slabs:
             s.ck(s.L.ek_halo_pack(s.h, phase, C.c_void_p(s.h_to_l.data_ptr()), C.c_void_p(s.h_to_r.data_ptr())), "ek_halo_pack")
-        self.comm.neighbor_exchange([s.h_to_l for s in self.slabs], [s.h_to_r for s in self.slabs],
-                                    [s.h_from_l for s in self.slabs], [s.h_from_r for s in self.slabs])
+        return self.comm.neighbor_exchange_start([s.h_to_l for s in self.slabs], [s.h_to_r for s in self.slabs],
+                                                 [s.h_from_l for s in self.slabs], [s.h_from_r for s in self.slabs])
+
+    def halo_exchange_finish(self, phase: int, handle):
+        self.comm.neighbor_exchange_finish(handle)
         for s in self.slabs:
             s.ck(s.L.ek_halo_unpack(s.h, phase, C.c_void_p(s.h_from_l.data_ptr()), C.c_void_p(s.h_from_r.data_ptr())), "ek_halo_unpack")
+
+    def halo_exchange(self, phase: int):
+        self.halo_exchange_finish(phase, self.halo_exchange_start(phase))
 
     def phi_halo_exchange(self):
         for s in self.slabs:
@@ -260,18 +305,38 @@ class SlabGroup:
             s.ck(s.L.ek_phi_halo_unpack(s.h, C.c_void_p(s.p_from_l.data_ptr()), C.c_void_p(s.p_from_r.data_ptr())), "ek_phi_halo_unpack")
 
     def poisson(self):
-        """the distributed fast_Poisson(): dq -> phi (interior, walls, ghost columns)"""
-        send = [s.poisson_forward_local() for s in self.slabs]
+        """the distributed fast_Poisson(): dq -> phi (interior, walls, ghost columns).
+        The planes are processed in `self.zchunks` chunks so that the all-to-all of
+        one chunk travels while the next chunk is being transformed."""
+        M = self.slabs[0].M
+        K = max(1, min(self.zchunks, M))
+        bounds = [(M * k // K, M * (k + 1) // K) for k in range(K)]
+        P = self.nranks
+        # y FFT + first transpose, chunk by chunk
+        pending = []
+        for (a, b) in bounds:
+            send = [s.poisson_forward_local(a, b) for s in self.slabs]
+            pending.append(self.comm.all_to_all_start(send))
         self._mark("poisson_y_fft_pack")
-        recv = self.comm.all_to_all(send)
-        self._mark("poisson_all_to_all_1")
-        send = [s.poisson_middle(r) for s, r in zip(self.slabs, recv)]
-        self._mark("poisson_x_fft_zsolve")
-        recv = self.comm.all_to_all(send)
-        self._mark("poisson_all_to_all_2")
-        for s, r in zip(self.slabs, recv):
-            s.poisson_backward_local(r)
-        self._mark("poisson_unpack_y_ifft")
+        Xs = [torch.empty((M, s.kyl, s.NXg), dtype=torch.complex128, device=s.dev) for s in self.slabs]
+        for (a, b), hnd in zip(bounds, pending):
+            recv = self.comm.all_to_all_finish(hnd)
+            for s, X, r in zip(self.slabs, Xs, recv):
+                X[a:b] = x_forward(r)
+        self._mark("poisson_all_to_all_1_x_fft")
+        for s, X in zip(self.slabs, Xs):
+            s.zsolve(X)
+        self._mark("poisson_zsolve")
+        pending = []
+        for (a, b) in bounds:
+            send = [x_backward(X[a:b], P) for X in Xs]
+            pending.append(self.comm.all_to_all_start(send))
+        self._mark("poisson_x_ifft_pack")
+        for k, ((a, b), hnd) in enumerate(zip(bounds, pending)):
+            recv = self.comm.all_to_all_finish(hnd)
+            for s, r in zip(self.slabs, recv):
+                s.poisson_backward_local(r, a, b, last=(k == K - 1))
+        self._mark("poisson_all_to_all_2_y_ifft")
         self.phi_halo_exchange()
         self._mark("phi_halo")
 
@@ -317,9 +382,13 @@ class SlabGroup:
             for s in self.slabs:
                 s.sim.stream_collide_save(full)
             self._mark("lbm")
-            self.halo_exchange(0 if parity == 0 else 1)
-            self._mark("population_halo")
+            # the populations travel while the Poisson stage computes (independent data)
+            phase = 0 if parity == 0 else 1
+            hnd = self.halo_exchange_start(phase)
+            self._mark("population_halo_pack")
             self.poisson()
+            self.halo_exchange_finish(phase, hnd)
+            self._mark("population_halo_unpack")
             if full:
                 for s in self.slabs:
                     s.ck(s.L.ek_compute_efield(s.h), "ek_compute_efield")
