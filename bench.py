@@ -5,8 +5,10 @@
 
 A "step" is one coupled time step (main.cu:189-200 of the reference): one fused
 LBM pass over the four D3Q27 population sets plus the spectral Poisson solve.
-N = 1 runs config C3 (EK-PNP + temperature, 256^3); N > 1 runs C4
-(1024x256x256) split into x-slabs, one rank per GPU (torchrun).
+N = 1 runs config C3 (EK-PNP + temperature, 256^3); N > 1 runs the C5 family
+weak-scaled, 1024*N x 512 x 256 split into x-slabs of 1024 columns, one rank per
+GPU (torchrun); N = 8 is config C5 (1.07 G cells).  --workload c4 runs the
+strong-scaling config C4 (1024x256x256) instead.
 
 value  = cells * K / device time of K steps (CUDA events on the stream the
          kernels are launched on, max over ranks), state resident in HBM.
@@ -46,6 +48,8 @@ WORKLOADS = {
                     "c_inf=0.002 so that the reference's PB start-up converges)"),
     "c4": dict(NX=1024, NY=256, NZ=256, over=dict(chargeinf=0.002, exf=2.0e6),
                name="C4 pressure- and electro-driven microchannel 1024x256x256, x-slabs (exf=2e6, c_inf=0.002)"),
+    "c5": dict(NX=8192, NY=512, NZ=256, over=dict(chargeinf=0.002, exf=2.0e6),
+               name="C5 long high-aspect-ratio microchannel 8192x512x256 (1.07 G cells), x-slabs (exf=2e6, c_inf=0.002)"),
     "c2": dict(NX=128, NY=64, NZ=64, over=dict(TH=0.0), name="C2 isothermal slit 128x64x64"),
     "c1": dict(NX=50, NY=8, NZ=51, over={}, name="C1 shipped 50x8x51"),
 }
@@ -237,7 +241,14 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     ek = importlib.import_module("ek-pnp-3d_b200")
-    wl = args.workload or ("c3" if world == 1 else "c4")
+    # N = 1: the named 1-GPU config C3.  N > 1: weak scaling in the C5 family, 1024*N x 512 x 256
+    # (134 M cells = 116 GB of populations per GPU; N = 8 is exactly BASELINE config C5).
+    # --workload c4 gives the strong-scaling series of config C4 instead.
+    wl = args.workload or ("c3" if world == 1 else "c5w")
+    if wl == "c5w":
+        WORKLOADS["c5w"] = dict(NX=1024 * world, NY=512, NZ=256, over=dict(chargeinf=0.002, exf=2.0e6), weak=True,
+                                name=f"C5 family, weak scaling: {1024 * world}x512x256 x-slabs of 1024 columns per GPU "
+                                     "(N=8 is config C5, 1.07 G cells; exf=2e6, c_inf=0.002)")
     w = WORKLOADS[wl]
     NX, NY, NZ = w["NX"], w["NY"], w["NZ"]
     mode = ek.STREAM_AA if args.stream_mode == "aa" else ek.STREAM_PUSH

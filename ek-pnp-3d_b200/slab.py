@@ -450,7 +450,8 @@ def bench_slabs(ek, dist, args, w, wl, local_rank):
     step_gbs = mlups * 1e6 * B_ALG_STEP / 1e9
     return {"metric": "coupled_step_mlups", "value": round(mlups, 2), "unit": "MLUPS", "n_gpus": comm.nranks,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4),
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak" if w.get("weak") else "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
             "config": {"workload": w["name"], "grid": [NX, NY, NZ], "stream_mode": "aa", "zchunk": args.zchunk,
                        "parallelism": f"x-slabs x{comm.nranks}: NCCL halo send/recv + all-to-all Poisson transposes",
                        "cells_per_gpu": cells // comm.nranks, "init": "reference start-up (PB iterations) %.2f s" % init_s,
