@@ -215,6 +215,7 @@ def main():
     ap.add_argument("--zchunk", type=int, default=32)
     ap.add_argument("--ref-all", action="store_true", help="reference arm: try every nThreads variant")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel", type=int, default=None, help="LBM kernel variant (ek_set_option kernel)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--pb-iters", type=int, default=501,
                     help="start-up Poisson-Boltzmann iterations (501 as the reference; lower only for profiling runs)")
@@ -265,6 +266,8 @@ def main():
     cells = NX * NY * NZ
     p = ek.default_params(NX=NX, NY=NY, NZ=NZ, pb_iters=args.pb_iters, **w["over"])
     sim = ek.Simulation(p, device=local_rank, stream_mode=mode, zchunk=args.zchunk)
+    if args.kernel is not None:
+        sim.set_option("kernel", args.kernel)
     t0 = time.time()
     sim.init()            # the reference's start-up: 501 Poisson-Boltzmann iterations + equilibrium
     sim.sync()

@@ -253,6 +253,11 @@ ek_status ek_set_option(ek_handle *h, const char *key, long long value)
         return EK_OK;
     }
     if (!strcmp(key, "profile")) { h->profile = value != 0; return EK_OK; }
+    if (!strcmp(key, "kernel")) {
+        if (value < 0 || value > 2) return EK_ERR_INVALID;
+        h->kernel = (int)value;
+        return EK_OK;
+    }
     if (!strcmp(key, "poisson_path")) {
         if (value != 0 && value != 1) return EK_ERR_INVALID;
         h->poisson_path = (int)value;
@@ -388,7 +393,9 @@ ek_status ek_stream_collide_save(ek_handle *h, int write_fields)
         EK_CUDA(h, cudaEventCreate(&e0)); EK_CUDA(h, cudaEventCreate(&e1));
         EK_CUDA(h, cudaEventRecord(e0, h->stream));
     }
-    EK_CUDA(h, ek_launch_step(a, mode, write_fields != 0, h->e_from_arrays, h->stream));
+    if (h->kernel == 1) EK_CUDA(h, ek_launch_step8(a, mode, write_fields != 0, h->e_from_arrays, h->stream));
+    else if (h->kernel == 2) EK_CUDA(h, ek_launch_step5(a, mode, write_fields != 0, h->e_from_arrays, h->stream));
+    else EK_CUDA(h, ek_launch_step(a, mode, write_fields != 0, h->e_from_arrays, h->stream));
     if (h->profile) {
         EK_CUDA(h, cudaEventRecord(e1, h->stream));
         h->ev_lbm.emplace_back(e0, e1);

@@ -45,6 +45,7 @@ struct ek_handle {
     bool e_from_arrays = false;    // next LBM pass takes E from the arrays, not from grad(phi)
     bool efield_stale = false;     // Ex/Ey/Ez arrays are older than phi (recomputed on demand)
     int zchunk = 32;
+    int kernel = 0;                // warps per 32 cells: 0 = four (ek_lbm.cu), 1 = eight (ek_lbm8.cu), 2 = five (ek_lbm.cu)
     int dc_mode = EK_DC_ZERO;
     int poisson_path = 0;          // 0: xy-FFT + tridiagonal z-solve, 1: odd-extension 3-D FFT
     double dc_ghat0 = 0.0;

@@ -26,7 +26,7 @@
 //  * a CTA walks a chunk of z so that the thread that owns the z = 0 node also
 //    owns z = 1: the bottom wall takes minus the z = 1 momentum (LBM.cu:663-801)
 //    and in an in-place scheme only the owner may read that node.
-#include "ek_internal.cuh"
+#include "ek_lbm_common.cuh"
 
 namespace {
 
@@ -34,126 +34,13 @@ struct Sh {
     double cp[32], cn[32], T[32];
     double E[3][32];
     double u[3][32];
+    // five-warp variant: partial moments of fluid half A, and rho / F for it
+    double rhoA[32], mpA[3][32], mnA[3][32];
+    double rho[32], F[3][32];
 };
 
-// Offsets of the 3x3x3 neighbourhood of a node.  Populations live in a tiled
-// layout per set, [z][y][x-tile][27 slots][32 lanes] (ek_internal.cuh): the slot
-// stride is a compile-time 256 B, so the 27 accesses of a node differ only by an
-// immediate and one 64-bit address per neighbour position is all the integer
-// work a gather or scatter needs.  Macroscopic fields stay in the reference's
-// [z][y][x] order (LBM.cu:22-25).
-struct Nbr {
-    unsigned lx[3], ly[3], lz[3];  // lattice element offsets of x-1,x,x+1 / y-1,y,y+1 / z-1,z,z+1 (z periodic)
-    int fx[3], fy[3], fz[3];       // the same for the field arrays
-    __device__ __forceinline__ unsigned at(int ax, int ay, int az) const { return lz[az + 1] + ly[ay + 1] + lx[ax + 1]; }
-    __device__ __forceinline__ unsigned lc() const { return lz[1] + ly[1] + lx[1]; }
-    __device__ __forceinline__ int fc() const { return fz[1] + fy[1] + fx[1]; }
-};
-
-__device__ __forceinline__ void set_xy(Nbr &nb, const EkConst &c, int x, int y)
-{
-    nb.fx[0] = x == 0 ? c.xlo : x - 1;
-    nb.fx[1] = x;
-    nb.fx[2] = x == c.NX - 1 ? c.xhi : x + 1;
-    const int ym = y == 0 ? c.NY - 1 : y - 1, yp = y == c.NY - 1 ? 0 : y + 1;
-    nb.fy[0] = ym * c.PX; nb.fy[1] = y * c.PX; nb.fy[2] = yp * c.PX;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) nb.lx[k] = ek_lat_col(nb.fx[k]);
-    nb.ly[0] = (unsigned)ym * c.lrow; nb.ly[1] = (unsigned)y * c.lrow; nb.ly[2] = (unsigned)yp * c.lrow;
-}
-
-__device__ __forceinline__ void set_z(Nbr &nb, const EkConst &c, int z)
-{
-    const int zm = z == 0 ? c.NZ - 1 : z - 1;
-    const int zp = z == c.NZ - 1 ? 0 : z + 1;
-    nb.fz[0] = (int)(zm * c.plane); nb.fz[1] = (int)(z * c.plane); nb.fz[2] = (int)(zp * c.plane);
-    nb.lz[0] = (unsigned)zm * c.lplane; nb.lz[1] = (unsigned)z * c.lplane; nb.lz[2] = (unsigned)zp * c.lplane;
-}
-
-__device__ __forceinline__ void bar_moments() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-__device__ __forceinline__ void bar_velocity() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
-
-// pre-collision populations of a node ("pull" restatement)
-template <int MODE>
-__device__ __forceinline__ void gather27(const double *lat, const Nbr &nb, double S[27])
-{
-    if (MODE == EK_MODE_AA_ODD) {
-#pragma unroll
-        for (int d = 0; d < 27; ++d) {
-            const double *q = lat + nb.at(-ek_cx(d), -ek_cy(d), -ek_cz(d));
-            S[d] = q[ek_opp(d) * EK_TILE];
-        }
-    } else {
-        const double *q = lat + nb.lc();
-#pragma unroll
-        for (int d = 0; d < 27; ++d) S[d] = q[d * EK_TILE];
-    }
-}
-
-// where the post-collision population of direction d goes
-template <int MODE, int d>
-__device__ __forceinline__ void put(double *lat, const Nbr &nb, double v)
-{
-    if (MODE == EK_MODE_AA_EVEN) {
-        double *q = lat + nb.lc();
-        q[ek_opp(d) * EK_TILE] = v;
-    } else {
-        double *q = lat + nb.at(ek_cx(d), ek_cy(d), ek_cz(d));
-        q[d * EK_TILE] = v;
-    }
-}
-
-// LBM.cu:621-630: left-to-right sum in index order
-__device__ __forceinline__ double sum27(const double S[27])
-{
-    double a = S[0];
-#pragma unroll
-    for (int d = 1; d < 27; ++d) a = a + S[d];
-    return a;
-}
-
-// LBM.cu:639-644: the three momentum brackets, grouped as in the reference
-__device__ __forceinline__ void momentum(const double f[27], double m[3])
-{
-    m[0] = (f[1] + f[7] + f[9] + f[13] + f[15] + f[19] + f[21] + f[23] + f[26]
-          - (f[2] + f[8] + f[10] + f[14] + f[16] + f[20] + f[22] + f[24] + f[25]));
-    m[1] = (f[3] + f[7] + f[11] + f[14] + f[17] + f[19] + f[21] + f[24] + f[25]
-          - (f[4] + f[8] + f[12] + f[13] + f[18] + f[20] + f[22] + f[23] + f[26]));
-    m[2] = (f[5] + f[9] + f[11] + f[16] + f[18] + f[19] + f[22] + f[23] + f[25]
-          - (f[6] + f[10] + f[12] + f[15] + f[17] + f[20] + f[21] + f[24] + f[26]));
-}
-
-template <int d>
-__device__ __forceinline__ double cdot(double ax, double ay, double az)
-{
-    double s = 0.0;
-    bool first = true;
-    if (ek_cx(d) != 0) { s = ek_cx(d) > 0 ? ax : -ax; first = false; }
-    if (ek_cy(d) != 0) { s = first ? (ek_cy(d) > 0 ? ay : -ay) : (ek_cy(d) > 0 ? s + ay : s - ay); first = false; }
-    if (ek_cz(d) != 0) { s = first ? (ek_cz(d) > 0 ? az : -az) : (ek_cz(d) > 0 ? s + az : s - az); }
-    return s;
-}
-
-// E = -grad phi with the reference's wall treatment (poisson.cu:40-69):
-// central differences, periodic x and y, Ez of the wall planes copied from
-// the first interior plane.
-template <bool EARR>
-__device__ __forceinline__ void efield_at(const StepArgs &a, const Nbr &nb, int z, double E[3])
-{
-    const EkConst &c = a.c;
-    if (EARR) {
-        const int i = nb.fc();
-        E[0] = a.E[0][i]; E[1] = a.E[1][i]; E[2] = a.E[2][i];
-    } else {
-        const double *phi = a.phi;
-        const int zb = nb.fz[1];
-        E[0] = 0.5 * (phi[zb + nb.fy[1] + nb.fx[0]] - phi[zb + nb.fy[1] + nb.fx[2]]) / c.dx;
-        E[1] = 0.5 * (phi[zb + nb.fy[0] + nb.fx[1]] - phi[zb + nb.fy[2] + nb.fx[1]]) / c.dy;
-        const int zc = z < 1 ? 1 : (z > c.NZ - 2 ? c.NZ - 2 : z);
-        const int col = nb.fy[1] + nb.fx[1];
-        E[2] = 0.5 * (phi[(size_t)(zc - 1) * c.plane + col] - phi[(size_t)(zc + 1) * c.plane + col]) / c.dz;
-    }
-}
+template <int NT> __device__ __forceinline__ void bar_moments() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
+template <int NT> __device__ __forceinline__ void bar_velocity() { asm volatile("bar.sync 2, %0;" ::"n"(NT) : "memory"); }
 
 // ---------------------------------------------------------------------------
 // scalar roles: cation (s = 1), anion (s = 2), temperature (s = 3)
@@ -220,7 +107,7 @@ struct ScalarPairs<MODE, 13> {
                                                bool) {}
 };
 
-template <int MODE, bool FULL, bool EARR>
+template <int MODE, bool FULL, bool EARR, int NT>
 __device__ __forceinline__ void scalar_role(const StepArgs &a, Sh &sh, const int s, const int lane, const bool act,
                                             Nbr &nb, const int pi, const int z0, const int z1)
 {
@@ -244,8 +131,8 @@ __device__ __forceinline__ void scalar_role(const StepArgs &a, Sh &sh, const int
             efield_at<EARR>(a, nb, 1, E);
             sh.E[0][lane] = E[0]; sh.E[1][lane] = E[1]; sh.E[2][lane] = E[2];
         }
-        bar_moments();
-        bar_velocity();
+        bar_moments<NT>();
+        bar_velocity<NT>();
     }
 
     for (int z = z0; z < z1; ++z) {
@@ -267,11 +154,11 @@ __device__ __forceinline__ void scalar_role(const StepArgs &a, Sh &sh, const int
             sh.E[0][lane] = E[0]; sh.E[1][lane] = E[1]; sh.E[2][lane] = E[2];
         }
         if (FULL && act) a.fld[3 + s][nb.fc()] = m;  // charge, chargen, T (LBM.cu:811-813)
-        bar_moments();
+        bar_moments<NT>();
         // E is read between the two barriers: the temperature warp may only
         // overwrite it after every warp has passed bar_velocity()
         if (!is_temp) { E[0] = sh.E[0][lane]; E[1] = sh.E[1][lane]; E[2] = sh.E[2][lane]; }
-        bar_velocity();
+        bar_velocity<NT>();
         double vx = sh.u[0][lane], vy = sh.u[1][lane], vz = sh.u[2][lane];
         if (!is_temp) {
             // ion drift u + K*E; Ext does not enter here (LBM.cu:851-862)
@@ -357,7 +244,7 @@ __device__ __forceinline__ void node_force_and_momentum(const EkConst &c, const 
     expr[2] = m[2] * c.cflinv + F[2] * c.dt * 0.5;
 }
 
-template <int MODE, bool FULL>
+template <int MODE, bool FULL, int NT>
 __device__ __forceinline__ void fluid_role(const StepArgs &a, Sh &sh, const int lane, const bool act, Nbr &nb,
                                            const int z0, const int z1)
 {
@@ -372,11 +259,11 @@ __device__ __forceinline__ void fluid_role(const StepArgs &a, Sh &sh, const int 
         gather27<MODE>(lin, nb, S);
         double m[3];
         momentum(S, m);
-        bar_moments();
+        bar_moments<NT>();
         const double E[3] = {sh.E[0][lane], sh.E[1][lane], sh.E[2][lane]};
         double F[3];
         node_force_and_momentum(c, m, sh.cp[lane] - sh.cn[lane], sh.T[lane], E, F, expr1);
-        bar_velocity();
+        bar_velocity<NT>();
     }
 
     for (int z = z0; z < z1; ++z) {
@@ -387,7 +274,7 @@ __device__ __forceinline__ void fluid_role(const StepArgs &a, Sh &sh, const int 
         const double rho = sum27(S);
         double m[3];
         momentum(S, m);
-        bar_moments();
+        bar_moments<NT>();
         const double E[3] = {sh.E[0][lane], sh.E[1][lane], sh.E[2][lane]};
         const double dq = sh.cp[lane] - sh.cn[lane];
         double F[3], ex_[3], u[3];
@@ -400,7 +287,7 @@ __device__ __forceinline__ void fluid_role(const StepArgs &a, Sh &sh, const int 
             u[0] = rhoinv * ex_[0]; u[1] = rhoinv * ex_[1]; u[2] = rhoinv * ex_[2];
         }
         sh.u[0][lane] = u[0]; sh.u[1][lane] = u[1]; sh.u[2][lane] = u[2];
-        bar_velocity();
+        bar_velocity<NT>();
         if (act) {
             const int i = nb.fc();
             a.dq[i] = dq;
@@ -439,8 +326,136 @@ __global__ void __launch_bounds__(128, 4) ek_step_kernel(const __grid_constant__
     Nbr nb;
     set_xy(nb, c, x, y);
     const int pi = y * c.PX + x;
-    if (role == 0) fluid_role<MODE, FULL>(a, sh, lane, act, nb, z0, z1);
-    else scalar_role<MODE, FULL, EARR>(a, sh, role, lane, act, nb, pi, z0, z1);
+    if (role == 0) fluid_role<MODE, FULL, 128>(a, sh, lane, act, nb, z0, z1);
+    else scalar_role<MODE, FULL, EARR, 128>(a, sh, role, lane, act, nb, pi, z0, z1);
+}
+
+// ---------------------------------------------------------------------------
+// Five warps per 32 cells: the fluid set is split over two warps (half A: rest +
+// pairs 1..6, half B: pairs 7..13) because the fluid warp of the four-warp kernel
+// carries ~1.75x the instructions of a scalar warp and everybody waits for it at
+// the barriers (ncu: 43 % of the warp stalls).  The sums are CHAINED from A to B
+// in the reference's order (LBM.cu:621-644), so the results are bit-identical to
+// the four-warp kernel.
+// ---------------------------------------------------------------------------
+template <int MODE, bool FULL, int NT>
+__device__ __forceinline__ void fluid_half_a(const StepArgs &a, Sh &sh, const int lane, const bool act, Nbr &nb,
+                                             const int z0, const int z1)
+{
+    const EkConst &c = a.c;
+    double *lin = a.in[0];
+    double *lout = a.out[0];
+    double S[13];
+    for (int zz = (z0 == 0 ? -1 : z0); zz < z1; ++zz) {
+        const bool pre = zz < 0;
+        const int z = pre ? 1 : zz;
+        set_z(nb, c, z);
+        const bool top = (z == c.NZ - 1);
+        const bool wall = (z == 0) || top;
+        gather_half<MODE, 0>(lin, nb, S);
+        sh.rhoA[lane] = sum_half<13>(S);
+        sh.mpA[0][lane] = S[1] + S[7] + S[9];   sh.mnA[0][lane] = S[2] + S[8] + S[10];
+        sh.mpA[1][lane] = S[3] + S[7] + S[11];  sh.mnA[1][lane] = S[4] + S[8] + S[12];
+        sh.mpA[2][lane] = S[5] + S[9] + S[11];  sh.mnA[2][lane] = S[6] + S[10] + S[12];
+        bar_moments<NT>();
+        bar_velocity<NT>();
+        if (pre) continue;
+        const double rho = sh.rho[lane];
+        const double u[3] = {sh.u[0][lane], sh.u[1][lane], sh.u[2][lane]};
+        const double F[3] = {sh.F[0][lane], sh.F[1][lane], sh.F[2][lane]};
+        if (FULL && act) {  // LBM.cu:807-810
+            const int i = nb.fc();
+            a.fld[0][i] = rho; a.fld[1][i] = u[0]; a.fld[2][i] = u[1]; a.fld[3][i] = u[2];
+        }
+        const double wcr[4] = {c.w[0] * rho, c.w[1] * rho, c.w[2] * rho, c.w[3] * rho};
+        const double omusq = 1.0 - 0.5 * (u[0] * u[0] + u[1] * u[1] + u[2] * u[2]) * c.inv_cs2;
+        const double uF = u[0] * F[0] + u[1] * F[1] + u[2] * F[2];
+        double O0 = S[0];
+        if (!wall) O0 = S[0] - c.wp[0] * (S[0] - wcr[0] * omusq) + c.dt * (c.sp * (-c.coe[0] * uF));
+        if (act) {
+            if (MODE == EK_MODE_PUSH) lout[nb.lc()] = O0;
+            else if (!wall) lout[nb.lc()] = O0;
+        }
+        FluidPairs8<MODE, 0, 0>::run(S, wcr, omusq, u, F, uF, wall, top, c, lout, nb, act);
+    }
+}
+
+template <int MODE, bool FULL, int NT>
+__device__ __forceinline__ void fluid_half_b(const StepArgs &a, Sh &sh, const int lane, const bool act, Nbr &nb,
+                                             const int z0, const int z1)
+{
+    const EkConst &c = a.c;
+    double *lin = a.in[0];
+    double *lout = a.out[0];
+    double S[14];
+    double expr1[3] = {0.0, 0.0, 0.0};
+#define F_(d) S[(d) - 13]
+    for (int zz = (z0 == 0 ? -1 : z0); zz < z1; ++zz) {
+        const bool pre = zz < 0;
+        const int z = pre ? 1 : zz;
+        set_z(nb, c, z);
+        const bool top = (z == c.NZ - 1);
+        const bool wall = (z == 0) || top;
+        gather_half<MODE, 1>(lin, nb, S);
+        bar_moments<NT>();
+        // continue half A's chains in the reference's order (LBM.cu:621-644)
+        double rho = sh.rhoA[lane];
+#pragma unroll
+        for (int i = 0; i < 14; ++i) rho = rho + S[i];
+        double m[3];
+        m[0] = (sh.mpA[0][lane] + F_(13) + F_(15) + F_(19) + F_(21) + F_(23) + F_(26)
+              - (sh.mnA[0][lane] + F_(14) + F_(16) + F_(20) + F_(22) + F_(24) + F_(25)));
+        m[1] = (sh.mpA[1][lane] + F_(14) + F_(17) + F_(19) + F_(21) + F_(24) + F_(25)
+              - (sh.mnA[1][lane] + F_(13) + F_(18) + F_(20) + F_(22) + F_(23) + F_(26)));
+        m[2] = (sh.mpA[2][lane] + F_(16) + F_(18) + F_(19) + F_(22) + F_(23) + F_(25)
+              - (sh.mnA[2][lane] + F_(15) + F_(17) + F_(20) + F_(21) + F_(24) + F_(26)));
+        const double E[3] = {sh.E[0][lane], sh.E[1][lane], sh.E[2][lane]};
+        const double dq = sh.cp[lane] - sh.cn[lane];
+        double F[3], ex_[3], u[3];
+        node_force_and_momentum(c, m, dq, sh.T[lane], E, F, ex_);
+        if (pre) {
+            expr1[0] = ex_[0]; expr1[1] = ex_[1]; expr1[2] = ex_[2];
+            bar_velocity<NT>();
+            continue;
+        }
+        const double rhoinv = 1.0 / rho;
+        if (z == 0) {
+            u[0] = -rhoinv * expr1[0]; u[1] = -rhoinv * expr1[1]; u[2] = -rhoinv * expr1[2];
+        } else {
+            u[0] = rhoinv * ex_[0]; u[1] = rhoinv * ex_[1]; u[2] = rhoinv * ex_[2];
+        }
+        sh.u[0][lane] = u[0]; sh.u[1][lane] = u[1]; sh.u[2][lane] = u[2];
+        sh.rho[lane] = rho;
+        sh.F[0][lane] = F[0]; sh.F[1][lane] = F[1]; sh.F[2][lane] = F[2];
+        bar_velocity<NT>();
+        if (act) a.dq[nb.fc()] = dq;
+        const double wcr[4] = {c.w[0] * rho, c.w[1] * rho, c.w[2] * rho, c.w[3] * rho};
+        const double omusq = 1.0 - 0.5 * (u[0] * u[0] + u[1] * u[1] + u[2] * u[2]) * c.inv_cs2;
+        const double uF = u[0] * F[0] + u[1] * F[1] + u[2] * F[2];
+        FluidPairs8<MODE, 1, 6>::run(S, wcr, omusq, u, F, uF, wall, top, c, lout, nb, act);
+    }
+#undef F_
+}
+
+template <int MODE, bool FULL, bool EARR>
+__global__ void __launch_bounds__(160, 3) ek_step5_kernel(const __grid_constant__ StepArgs a)
+{
+    __shared__ Sh sh;
+    const EkConst &c = a.c;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    int x = blockIdx.x * 32 + lane;
+    const bool act = x < c.NX;
+    if (!act) x = c.NX - 1;
+    const int y = blockIdx.y;
+    const int z0 = blockIdx.z * a.zchunk;
+    const int z1 = min(z0 + a.zchunk, c.NZ);
+    Nbr nb;
+    set_xy(nb, c, x, y);
+    const int pi = y * c.PX + x;
+    if (warp == 0) fluid_half_a<MODE, FULL, 160>(a, sh, lane, act, nb, z0, z1);
+    else if (warp == 1) fluid_half_b<MODE, FULL, 160>(a, sh, lane, act, nb, z0, z1);
+    else scalar_role<MODE, FULL, EARR, 160>(a, sh, warp - 1, lane, act, nb, pi, z0, z1);
 }
 
 // natural-layout export of the pre-collision state (tests, checkpoints)
@@ -470,6 +485,19 @@ __global__ void ek_export_kernel(const StepArgs a, int s, double *dst)
 }
 
 template <int MODE>
+cudaError_t launch_mode5(const StepArgs &a, bool full, bool earr, dim3 grid, cudaStream_t st)
+{
+    if (full) {
+        if (earr) ek_step5_kernel<MODE, true, true><<<grid, 160, 0, st>>>(a);
+        else ek_step5_kernel<MODE, true, false><<<grid, 160, 0, st>>>(a);
+    } else {
+        if (earr) ek_step5_kernel<MODE, false, true><<<grid, 160, 0, st>>>(a);
+        else ek_step5_kernel<MODE, false, false><<<grid, 160, 0, st>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+template <int MODE>
 cudaError_t launch_mode(const StepArgs &a, bool full, bool earr, dim3 grid, cudaStream_t st)
 {
     if (full) {
@@ -492,6 +520,17 @@ cudaError_t ek_launch_step(const StepArgs &a, int mode, bool write_fields, bool 
     case EK_MODE_AA_EVEN: return launch_mode<EK_MODE_AA_EVEN>(a, write_fields, e_from_arrays, grid, st);
     case EK_MODE_AA_ODD: return launch_mode<EK_MODE_AA_ODD>(a, write_fields, e_from_arrays, grid, st);
     default: return launch_mode<EK_MODE_PUSH>(a, write_fields, e_from_arrays, grid, st);
+    }
+}
+
+cudaError_t ek_launch_step5(const StepArgs &a, int mode, bool write_fields, bool e_from_arrays, cudaStream_t st)
+{
+    const EkConst &c = a.c;
+    dim3 grid((c.NX + 31) / 32, c.NY, (c.NZ + a.zchunk - 1) / a.zchunk);
+    switch (mode) {
+    case EK_MODE_AA_EVEN: return launch_mode5<EK_MODE_AA_EVEN>(a, write_fields, e_from_arrays, grid, st);
+    case EK_MODE_AA_ODD: return launch_mode5<EK_MODE_AA_ODD>(a, write_fields, e_from_arrays, grid, st);
+    default: return launch_mode5<EK_MODE_PUSH>(a, write_fields, e_from_arrays, grid, st);
     }
 }
 

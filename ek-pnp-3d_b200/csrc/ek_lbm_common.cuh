@@ -1,0 +1,211 @@
+// ek_lbm_common.cuh -- device helpers shared by the step kernels (ek_lbm.cu:
+// four warps per 32 cells; ek_lbm8.cu: eight warps per 32 cells).
+#pragma once
+
+#include "ek_internal.cuh"
+
+namespace {
+
+// Offsets of the 3x3x3 neighbourhood of a node.  Populations live in a tiled
+// layout per set, [z][y][x-tile][27 slots][32 lanes] (ek_internal.cuh): the slot
+// stride is a compile-time 256 B, so the 27 accesses of a node differ only by an
+// immediate and one 64-bit address per neighbour position is all the integer
+// work a gather or scatter needs.  Macroscopic fields stay in the reference's
+// [z][y][x] order (LBM.cu:22-25).
+struct Nbr {
+    unsigned lx[3], ly[3], lz[3];  // lattice element offsets of x-1,x,x+1 / y-1,y,y+1 / z-1,z,z+1 (z periodic)
+    int fx[3], fy[3], fz[3];       // the same for the field arrays
+    __device__ __forceinline__ unsigned at(int ax, int ay, int az) const { return lz[az + 1] + ly[ay + 1] + lx[ax + 1]; }
+    __device__ __forceinline__ unsigned lc() const { return lz[1] + ly[1] + lx[1]; }
+    __device__ __forceinline__ int fc() const { return fz[1] + fy[1] + fx[1]; }
+};
+
+__device__ __forceinline__ void set_xy(Nbr &nb, const EkConst &c, int x, int y)
+{
+    nb.fx[0] = x == 0 ? c.xlo : x - 1;
+    nb.fx[1] = x;
+    nb.fx[2] = x == c.NX - 1 ? c.xhi : x + 1;
+    const int ym = y == 0 ? c.NY - 1 : y - 1, yp = y == c.NY - 1 ? 0 : y + 1;
+    nb.fy[0] = ym * c.PX; nb.fy[1] = y * c.PX; nb.fy[2] = yp * c.PX;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) nb.lx[k] = ek_lat_col(nb.fx[k]);
+    nb.ly[0] = (unsigned)ym * c.lrow; nb.ly[1] = (unsigned)y * c.lrow; nb.ly[2] = (unsigned)yp * c.lrow;
+}
+
+__device__ __forceinline__ void set_z(Nbr &nb, const EkConst &c, int z)
+{
+    const int zm = z == 0 ? c.NZ - 1 : z - 1;
+    const int zp = z == c.NZ - 1 ? 0 : z + 1;
+    nb.fz[0] = (int)(zm * c.plane); nb.fz[1] = (int)(z * c.plane); nb.fz[2] = (int)(zp * c.plane);
+    nb.lz[0] = (unsigned)zm * c.lplane; nb.lz[1] = (unsigned)z * c.lplane; nb.lz[2] = (unsigned)zp * c.lplane;
+}
+
+// pre-collision populations of a node ("pull" restatement)
+template <int MODE>
+__device__ __forceinline__ void gather27(const double *lat, const Nbr &nb, double S[27])
+{
+    if (MODE == EK_MODE_AA_ODD) {
+#pragma unroll
+        for (int d = 0; d < 27; ++d) {
+            const double *q = lat + nb.at(-ek_cx(d), -ek_cy(d), -ek_cz(d));
+            S[d] = q[ek_opp(d) * EK_TILE];
+        }
+    } else {
+        const double *q = lat + nb.lc();
+#pragma unroll
+        for (int d = 0; d < 27; ++d) S[d] = q[d * EK_TILE];
+    }
+}
+
+// where the post-collision population of direction d goes
+template <int MODE, int d>
+__device__ __forceinline__ void put(double *lat, const Nbr &nb, double v)
+{
+    if (MODE == EK_MODE_AA_EVEN) {
+        double *q = lat + nb.lc();
+        q[ek_opp(d) * EK_TILE] = v;
+    } else {
+        double *q = lat + nb.at(ek_cx(d), ek_cy(d), ek_cz(d));
+        q[d * EK_TILE] = v;
+    }
+}
+
+// LBM.cu:621-630: left-to-right sum in index order
+__device__ __forceinline__ double sum27(const double S[27])
+{
+    double a = S[0];
+#pragma unroll
+    for (int d = 1; d < 27; ++d) a = a + S[d];
+    return a;
+}
+
+// LBM.cu:639-644: the three momentum brackets, grouped as in the reference
+__device__ __forceinline__ void momentum(const double f[27], double m[3])
+{
+    m[0] = (f[1] + f[7] + f[9] + f[13] + f[15] + f[19] + f[21] + f[23] + f[26]
+          - (f[2] + f[8] + f[10] + f[14] + f[16] + f[20] + f[22] + f[24] + f[25]));
+    m[1] = (f[3] + f[7] + f[11] + f[14] + f[17] + f[19] + f[21] + f[24] + f[25]
+          - (f[4] + f[8] + f[12] + f[13] + f[18] + f[20] + f[22] + f[23] + f[26]));
+    m[2] = (f[5] + f[9] + f[11] + f[16] + f[18] + f[19] + f[22] + f[23] + f[25]
+          - (f[6] + f[10] + f[12] + f[15] + f[17] + f[20] + f[21] + f[24] + f[26]));
+}
+
+template <int d>
+__device__ __forceinline__ double cdot(double ax, double ay, double az)
+{
+    double s = 0.0;
+    bool first = true;
+    if (ek_cx(d) != 0) { s = ek_cx(d) > 0 ? ax : -ax; first = false; }
+    if (ek_cy(d) != 0) { s = first ? (ek_cy(d) > 0 ? ay : -ay) : (ek_cy(d) > 0 ? s + ay : s - ay); first = false; }
+    if (ek_cz(d) != 0) { s = first ? (ek_cz(d) > 0 ? az : -az) : (ek_cz(d) > 0 ? s + az : s - az); }
+    return s;
+}
+
+// E = -grad phi with the reference's wall treatment (poisson.cu:40-69):
+// central differences, periodic x and y, Ez of the wall planes copied from
+// the first interior plane.
+template <bool EARR>
+__device__ __forceinline__ void efield_at(const StepArgs &a, const Nbr &nb, int z, double E[3])
+{
+    const EkConst &c = a.c;
+    if (EARR) {
+        const int i = nb.fc();
+        E[0] = a.E[0][i]; E[1] = a.E[1][i]; E[2] = a.E[2][i];
+    } else {
+        const double *phi = a.phi;
+        const int zb = nb.fz[1];
+        E[0] = 0.5 * (phi[zb + nb.fy[1] + nb.fx[0]] - phi[zb + nb.fy[1] + nb.fx[2]]) / c.dx;
+        E[1] = 0.5 * (phi[zb + nb.fy[0] + nb.fx[1]] - phi[zb + nb.fy[2] + nb.fx[1]]) / c.dy;
+        const int zc = z < 1 ? 1 : (z > c.NZ - 2 ? c.NZ - 2 : z);
+        const int col = nb.fy[1] + nb.fx[1];
+        E[2] = 0.5 * (phi[(size_t)(zc - 1) * c.plane + col] - phi[(size_t)(zc + 1) * c.plane + col]) / c.dz;
+    }
+}
+
+
+// ---- a population set split over two warps: half A = rest + pairs 1..6 (slots
+// 0..12), half B = pairs 7..13 (slots 13..26)
+template <int HALF> struct Half;
+template <> struct Half<0> { static constexpr int D0 = 0, ND = 13, P0 = 0, P1 = 6; };
+template <> struct Half<1> { static constexpr int D0 = 13, ND = 14, P0 = 6, P1 = 13; };
+
+template <int MODE, int HALF>
+__device__ __forceinline__ void gather_half(const double *lat, const Nbr &nb, double *S)
+{
+    constexpr int D0 = Half<HALF>::D0, ND = Half<HALF>::ND;
+    if (MODE == EK_MODE_AA_ODD) {
+#pragma unroll
+        for (int i = 0; i < ND; ++i) {
+            const int d = D0 + i;
+            const double *q = lat + nb.at(-ek_cx(d), -ek_cy(d), -ek_cz(d));
+            S[i] = q[ek_opp(d) * EK_TILE];
+        }
+    } else {
+        const double *q = lat + nb.lc();
+#pragma unroll
+        for (int i = 0; i < ND; ++i) S[i] = q[(D0 + i) * EK_TILE];
+    }
+}
+
+template <int ND>
+__device__ __forceinline__ double sum_half(const double *S)
+{
+    double a = S[0];
+#pragma unroll
+    for (int i = 1; i < ND; ++i) a = a + S[i];
+    return a;
+}
+
+
+// ------------------------------------------------------------------ fluid
+template <int MODE, int HALF, int p>
+struct FluidPairs8 {
+    static __device__ __forceinline__ void run(const double *S, const double wcr[4], double omusq, const double u[3],
+                                               const double F[3], double uF, bool wall, bool top, const EkConst &c,
+                                               double *lout, const Nbr &nb, bool act)
+    {
+        constexpr int D0 = Half<HALF>::D0;
+        constexpr int d = 2 * p + 1, o = d + 1, cls = ek_wclass(d);
+        double Oa, Ob;
+        if (!wall) {
+            const double cu = cdot<d>(u[0], u[1], u[2]);
+            const double cF = cdot<d>(F[0], F[1], F[2]);
+            const double s_ = cu * c.tfac;
+            const double wr = wcr[cls];
+            const double ep = wr * (omusq + 0.5 * s_ * s_);
+            const double em = wr * s_;
+            const double a = S[d - D0], b = S[o - D0];
+            const double np_ = c.wp[0] * (0.5 * (a + b) - ep);
+            const double nm_ = c.wm[0] * (0.5 * (a - b) - em);
+            const double Fp = c.sp * (c.coe[cls] * (cu * cF * c.cflinv2 - uF));
+            const double Fm = c.sm * (c.coe[cls] * c.cflinv * cF);
+            Oa = a - (np_ + nm_) + c.dt * (Fp + Fm);
+            Ob = b - (np_ - nm_) + c.dt * (Fp - Fm);
+        } else {
+            Oa = S[o - D0];
+            Ob = S[d - D0];
+            if (top) {
+                if (ek_uwsign(d) > 0) Oa = Oa + c.multi[cls]; else if (ek_uwsign(d) < 0) Oa = Oa - c.multi[cls];
+                if (ek_uwsign(o) > 0) Ob = Ob + c.multi[cls]; else if (ek_uwsign(o) < 0) Ob = Ob - c.multi[cls];
+            }
+        }
+        if (act) {
+            put<MODE, d>(lout, nb, Oa);
+            put<MODE, o>(lout, nb, Ob);
+        }
+        FluidPairs8<MODE, HALF, p + 1>::run(S, wcr, omusq, u, F, uF, wall, top, c, lout, nb, act);
+    }
+};
+template <int MODE>
+struct FluidPairs8<MODE, 0, 6> {
+    static __device__ __forceinline__ void run(const double *, const double *, double, const double *, const double *,
+                                               double, bool, bool, const EkConst &, double *, const Nbr &, bool) {}
+};
+template <int MODE>
+struct FluidPairs8<MODE, 1, 13> {
+    static __device__ __forceinline__ void run(const double *, const double *, double, const double *, const double *,
+                                               double, bool, bool, const EkConst &, double *, const Nbr &, bool) {}
+};
+
+
+}  // namespace

@@ -421,3 +421,31 @@ def test_reference_signature_shim(ek):
     got = {k: v.cpu().numpy() for k, v in arr.items()}
     want, _ = oracle_run(over, init, steps)
     check(util.field_errors(got, want))
+
+
+def test_kernel_variants_agree(ek):
+    """four-, five- and eight-warp step kernels: 0 and 2 chain the sums in the
+    reference's order and must agree bit for bit; 1 adds two partial sums."""
+    over = dict(NX=40, NY=5, NZ=21, uw=1.0e-4, exf=1.0e6)
+    init = synthetic_init(over)
+    res = {}
+    for kernel in (0, 1, 2):
+        for mode in (ek.STREAM_AA, ek.STREAM_PUSH):
+            sim = ek.Simulation(ek.default_params(**over), stream_mode=mode, zchunk=6)
+            sim.set_option("kernel", kernel)
+            sim.set_fields(init)
+            sim.init_equilibrium()
+            sim.step(7)
+            res[kernel, mode] = (sim.fields(), np.stack([sim.populations(s) for s in range(4)]))
+            sim.close()
+    base_f, base_p = res[0, ek.STREAM_AA]
+    for key in ((0, ek.STREAM_PUSH), (2, ek.STREAM_AA), (2, ek.STREAM_PUSH)):
+        f, p = res[key]
+        for k in util.FIELDS:
+            assert np.array_equal(f[k], base_f[k]), (key, k)
+        assert np.array_equal(p, base_p), key
+    for key in ((1, ek.STREAM_AA), (1, ek.STREAM_PUSH)):
+        check(util.field_errors(res[key][0], base_f))
+    want, _ = oracle_run(over, init, 7)
+    for key in res:
+        check(util.field_errors(res[key][0], want))
