@@ -82,6 +82,8 @@ def load_library():
     L.ek_step.argtypes = [H, C.c_int]
     L.ek_step_timed.argtypes = [H, C.c_int, C.POINTER(C.c_float)]
     L.ek_stream_collide_save.argtypes = [H, C.c_int]
+    L.ek_stream_collide_save_range.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.ek_switch_stream.argtypes = [H, C.c_void_p]
     L.ek_fast_poisson.argtypes = [H, C.c_int]
     L.ek_get_field.argtypes = [H, C.c_int, C.c_void_p, C.c_int]
     L.ek_field_ptr.argtypes = [H, C.c_int, C.POINTER(C.c_void_p)]

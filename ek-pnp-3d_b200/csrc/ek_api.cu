@@ -383,10 +383,23 @@ ek_status ek_init(ek_handle *h)
 
 ek_status ek_stream_collide_save(ek_handle *h, int write_fields)
 {
+    return ek_stream_collide_save_range(h, write_fields, 0, 0, 1);
+}
+
+// One LBM pass restricted to the z-chunks [zblock0, zblock1) (chunks of "zchunk"
+// planes; 0,0 = everything).  The launches of one pass may be issued in any
+// order and on different streams (the A-A access sets of different nodes are
+// disjoint); `last` != 0 on the final launch of the pass advances the parity.
+ek_status ek_stream_collide_save_range(ek_handle *h, int write_fields, int zblock0, int zblock1, int last)
+{
     if (!h) return EK_ERR_INVALID;
     if (!h->pops_ready) { ek_set_error(h, "ek_stream_collide_save before ek_init_equilibrium"); return EK_ERR_STATE; }
+    const int nblocks = (h->c.NZ + h->zchunk - 1) / h->zchunk;
+    if (zblock0 < 0 || zblock1 > nblocks || (zblock1 != 0 && zblock1 <= zblock0)) return EK_ERR_INVALID;
     DeviceGuard g(h->device);
     StepArgs a = ek_step_args(h);
+    a.zblock0 = zblock0;
+    a.nzblocks = zblock1 > 0 ? zblock1 - zblock0 : 0;
     const int mode = h->stream_mode == EK_STREAM_PUSH ? EK_MODE_PUSH : (h->parity ? EK_MODE_AA_ODD : EK_MODE_AA_EVEN);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->profile) {
@@ -401,7 +414,9 @@ ek_status ek_stream_collide_save(ek_handle *h, int write_fields)
         h->ev_lbm.emplace_back(e0, e1);
     }
     h->lbm_launches += 1;
-    if (h->stream_mode == EK_STREAM_PUSH) h->cur ^= 1; else h->parity ^= 1;
+    if (last) {
+        if (h->stream_mode == EK_STREAM_PUSH) h->cur ^= 1; else h->parity ^= 1;
+    }
     return EK_OK;
 }
 

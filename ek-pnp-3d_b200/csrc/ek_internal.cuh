@@ -98,6 +98,7 @@ struct StepArgs {
     double *dq;           // c+ - c- for the Poisson stage
     double *fld[7];       // rho ux uy uz charge chargen T (only when fields are written)
     int zchunk;
+    int zblock0, nzblocks;  // sub-range of z-chunks for this launch (nzblocks = 0: all)
 };
 
 // ---------------------------------------------------------------------------

@@ -108,9 +108,12 @@ struct ScalarPairs8 {
                     put<MODE, d>(lout, nb, Oa);
                     put<MODE, o>(lout, nb, Ob);
                 } else {
-                    const int za = z + ek_cz(d), zb = z - ek_cz(d);
-                    if (ek_cz(d) == 0 || !(za == 0 || za == c.NZ - 1)) put<MODE, d>(lout, nb, Oa);
-                    if (ek_cz(d) == 0 || !(zb == 0 || zb == c.NZ - 1)) put<MODE, o>(lout, nb, Ob);
+                    // z is interior here: the target z +- 1 is a wall plane only next to a wall
+                    const bool near_bottom = (z == 1), near_top = (z == c.NZ - 2);
+                    const bool drop_a = ek_cz(d) > 0 ? near_top : (ek_cz(d) < 0 ? near_bottom : false);
+                    const bool drop_b = ek_cz(d) > 0 ? near_bottom : (ek_cz(d) < 0 ? near_top : false);
+                    if (!drop_a) put<MODE, d>(lout, nb, Oa);
+                    if (!drop_b) put<MODE, o>(lout, nb, Ob);
                 }
             } else {
                 if (ek_cz(d) != 0) {
@@ -271,7 +274,7 @@ __global__ void __launch_bounds__(256, 3) ek_step8_kernel(const __grid_constant_
     const bool act = x < c.NX;
     if (!act) x = c.NX - 1;  // clamped duplicate: loads stay in bounds, stores are masked
     const int y = blockIdx.y;
-    const int z0 = blockIdx.z * a.zchunk;
+    const int z0 = (blockIdx.z + a.zblock0) * a.zchunk;
     const int z1 = min(z0 + a.zchunk, c.NZ);
     Nbr nb;
     set_xy(nb, c, x, y);
@@ -298,7 +301,7 @@ cudaError_t launch_mode8(const StepArgs &a, bool full, bool earr, dim3 grid, cud
 cudaError_t ek_launch_step8(const StepArgs &a, int mode, bool write_fields, bool e_from_arrays, cudaStream_t st)
 {
     const EkConst &c = a.c;
-    dim3 grid((c.NX + 31) / 32, c.NY, (c.NZ + a.zchunk - 1) / a.zchunk);
+    dim3 grid((c.NX + 31) / 32, c.NY, a.nzblocks > 0 ? a.nzblocks : (c.NZ + a.zchunk - 1) / a.zchunk);
     switch (mode) {
     case EK_MODE_AA_EVEN: return launch_mode8<EK_MODE_AA_EVEN>(a, write_fields, e_from_arrays, grid, st);
     case EK_MODE_AA_ODD: return launch_mode8<EK_MODE_AA_ODD>(a, write_fields, e_from_arrays, grid, st);

@@ -94,6 +94,13 @@ ek_status ek_set_stream(ek_handle *h, void *stream)
     return EK_OK;
 }
 
+ek_status ek_switch_stream(ek_handle *h, void *stream)
+{
+    if (!h || h->own_stream) return EK_ERR_STATE;
+    h->stream = (cudaStream_t)stream;
+    return EK_OK;
+}
+
 long long ek_halo_doubles(ek_handle *h) { return h ? (long long)4 * 9 * h->c.NY * h->c.NZ : 0; }
 int ek_lbm_parity(ek_handle *h) { return h ? h->parity : -1; }
 
@@ -208,17 +215,20 @@ ek_status ek_zsolve_columns(ek_handle *h, double *spec, int ky0, int kyl)
 }
 
 // After the host wrote the interior planes of phi: wall planes, flags, E arrays.
-ek_status ek_poisson_finish(ek_handle *h, int write_efield)
+ek_status ek_poisson_finish(ek_handle *h, int set_walls)
 {
     if (!h) return EK_ERR_INVALID;
     if (!h->allocated) return EK_ERR_STATE;
     DeviceGuard g(h->device);
-    ek_launch_set_walls(h->c, h->fld[EK_PHI], h->stream);
-    h->poisson_launches += 1;
+    if (set_walls) {
+        // only needed when something other than the solver touched phi (start-up
+        // relaxation, uploads): the solver itself never writes the wall planes
+        ek_launch_set_walls(h->c, h->fld[EK_PHI], h->stream);
+        h->poisson_launches += 1;
+        EK_CUDA(h, cudaGetLastError());
+    }
     h->e_from_arrays = false;
     h->efield_stale = true;
-    (void)write_efield;
-    EK_CUDA(h, cudaGetLastError());
     return EK_OK;
 }
 

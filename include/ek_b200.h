@@ -101,6 +101,10 @@ ek_status ek_step(ek_handle *h, int nsteps);
  * one LBM pass that leaves c+ - c- for the solver, then the solve. */
 ek_status ek_stream_collide_save(ek_handle *h, int write_fields);
 ek_status ek_fast_poisson(ek_handle *h, int write_efield);
+/* the LBM pass split into launches over z-chunk ranges [zblock0, zblock1) of
+ * "zchunk" planes each (0,0 = all); last != 0 on the final launch of a pass.
+ * Lets the host pipeline the distributed Poisson stage against the LBM pass. */
+ek_status ek_stream_collide_save_range(ek_handle *h, int write_fields, int zblock0, int zblock1, int last);
 
 /* ek_step bracketed by CUDA events on the handle's stream; blocks until done
  * and returns the device time of the nsteps steps in milliseconds. */
@@ -178,6 +182,8 @@ ek_status ek_save_data_end(ek_handle *h, const char *path, double time);
 ek_status ek_create_slab(const ek_params *global, int device, int rank, int nranks, ek_handle **out);
 /* run on a caller-provided cudaStream_t (e.g. torch's current stream) */
 ek_status ek_set_stream(ek_handle *h, void *stream);
+/* switch streams without draining the old one (the caller orders them with events) */
+ek_status ek_switch_stream(ek_handle *h, void *stream);
 ek_status ek_ensure_allocated(ek_handle *h);
 int ek_row_pitch(ek_handle *h);          /* doubles per row of a field array (>= NX, ghosts included) */
 int ek_lbm_parity(ek_handle *h);         /* 1 after an even (local) A-A step, 0 after an odd one */
@@ -195,7 +201,7 @@ ek_status ek_phi_halo_unpack(ek_handle *h, const double *from_left, const double
  * (wall planes of phi, flags) once the host has written phi's interior */
 ek_status ek_dq_ptr(ek_handle *h, double **dev_ptr);
 ek_status ek_zsolve_columns(ek_handle *h, double *spec, int ky0, int kyl);
-ek_status ek_poisson_finish(ek_handle *h, int write_efield);
+ek_status ek_poisson_finish(ek_handle *h, int set_walls);
 ek_status ek_compute_efield(ek_handle *h);
 /* the pieces of initialization() (LBM.cu:68-146) for a host-driven PB loop */
 ek_status ek_init_uniform(ek_handle *h);
