@@ -254,7 +254,9 @@ ek_status ek_set_option(ek_handle *h, const char *key, long long value)
     }
     if (!strcmp(key, "profile")) { h->profile = value != 0; return EK_OK; }
     if (!strcmp(key, "kernel")) {
-        if (value < 0 || value > 2) return EK_ERR_INVALID;
+        // 0: four warps, lean deep-interior path (default); 1: eight warps; 2: five warps;
+        // 3: four warps, general path everywhere (cross-check of the lean path)
+        if (value < 0 || value > 3) return EK_ERR_INVALID;
         h->kernel = (int)value;
         return EK_OK;
     }
@@ -355,6 +357,7 @@ ek_status ek_set_fields(ek_handle *h, const double *const fields[EK_NFIELDS], in
     h->fields_ready = true;
     h->pops_ready = false;
     h->e_from_arrays = true;
+    if (fields[EK_PHI]) h->phi_walls_dirty = true;
     return EK_OK;
 }
 
@@ -408,7 +411,7 @@ ek_status ek_stream_collide_save_range(ek_handle *h, int write_fields, int zbloc
     }
     if (h->kernel == 1) EK_CUDA(h, ek_launch_step8(a, mode, write_fields != 0, h->e_from_arrays, h->stream));
     else if (h->kernel == 2) EK_CUDA(h, ek_launch_step5(a, mode, write_fields != 0, h->e_from_arrays, h->stream));
-    else EK_CUDA(h, ek_launch_step(a, mode, write_fields != 0, h->e_from_arrays, h->stream));
+    else EK_CUDA(h, ek_launch_step(a, mode, write_fields != 0, h->e_from_arrays, h->kernel != 3, h->stream));
     if (h->profile) {
         EK_CUDA(h, cudaEventRecord(e1, h->stream));
         h->ev_lbm.emplace_back(e0, e1);
@@ -494,6 +497,7 @@ ek_status ek_adopt_field(ek_handle *h, int id, double *dev_ptr)
     if (!h->fld_external[id]) cudaFree(h->fld[id]);
     h->fld[id] = dev_ptr;
     h->fld_external[id] = true;
+    if (id == EK_PHI) h->phi_walls_dirty = true;
     return EK_OK;
 }
 

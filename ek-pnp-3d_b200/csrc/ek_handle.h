@@ -44,8 +44,9 @@ struct ek_handle {
     bool pops_ready = false;       // populations initialised
     bool e_from_arrays = false;    // next LBM pass takes E from the arrays, not from grad(phi)
     bool efield_stale = false;     // Ex/Ey/Ez arrays are older than phi (recomputed on demand)
+    bool phi_walls_dirty = true;   // something other than the solver wrote phi: its wall planes must be re-imposed
     int zchunk = 32;
-    int kernel = 0;                // warps per 32 cells: 0 = four (ek_lbm.cu), 1 = eight (ek_lbm8.cu), 2 = five (ek_lbm.cu)
+    int kernel = 0;                // 0 = four warps + lean interior path, 1 = eight warps, 2 = five warps, 3 = four warps, general path only
     int dc_mode = EK_DC_ZERO;
     int poisson_path = 0;          // 0: xy-FFT + tridiagonal z-solve, 1: odd-extension 3-D FFT
     double dc_ghat0 = 0.0;

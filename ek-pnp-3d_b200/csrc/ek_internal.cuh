@@ -158,7 +158,8 @@ void ek_launch_set_walls(const EkConst &c, double *phi, cudaStream_t st);
 // ---------------------------------------------------------------------------
 // LBM stage (ek_lbm.cu) and start-up kernels (ek_init.cu)
 // ---------------------------------------------------------------------------
-cudaError_t ek_launch_step(const StepArgs &a, int mode, bool write_fields, bool e_from_arrays, cudaStream_t st);
+cudaError_t ek_launch_step(const StepArgs &a, int mode, bool write_fields, bool e_from_arrays, bool lean,
+                           cudaStream_t st);
 cudaError_t ek_launch_step5(const StepArgs &a, int mode, bool write_fields, bool e_from_arrays, cudaStream_t st);
 cudaError_t ek_launch_step8(const StepArgs &a, int mode, bool write_fields, bool e_from_arrays, cudaStream_t st);
 cudaError_t ek_launch_export(const StepArgs &a, int mode, int set, double *dst, cudaStream_t st);

@@ -45,14 +45,14 @@ template <int NT> __device__ __forceinline__ void bar_velocity() { asm volatile(
 // ---------------------------------------------------------------------------
 // scalar roles: cation (s = 1), anion (s = 2), temperature (s = 3)
 // ---------------------------------------------------------------------------
-template <int MODE, int p>
+template <int MODE, bool LEAN, int p>
 struct ScalarPairs {
     // TRT relaxation of the opposite pair (d, d+1), d = 2p+1 (LBM.cu:1148-1845),
     // then delivery of both results.
     static __device__ __forceinline__ void run(const double S[27], double wcm[4], double omusq, double vtx, double vty,
                                                double vtz, double wp, double wmn, bool wall, bool bottom, bool is_temp,
-                                               const EkConst &c, double *lout, const Nbr &nb, int z, double *Wn,
-                                               bool act)
+                                               const EkConst &c, double *lout, const Nbr &nb, const LeanAddr &la, int z,
+                                               double *Wn, bool act)
     {
         constexpr int d = 2 * p + 1, o = d + 1, cls = ek_wclass(d);
         const double s_ = cdot<d>(vtx, vty, vtz);
@@ -65,7 +65,10 @@ struct ScalarPairs {
         const double Oa = a - (np_ + nm_);
         const double Ob = b - (np_ - nm_);
         if (act) {
-            if (!wall) {
+            if (LEAN) {
+                putx<MODE, d, true>(lout, nb, la, Oa);
+                putx<MODE, o, true>(lout, nb, la, Ob);
+            } else if (!wall) {
                 if (MODE == EK_MODE_AA_EVEN) {
                     put<MODE, d>(lout, nb, Oa);
                     put<MODE, o>(lout, nb, Ob);
@@ -99,35 +102,102 @@ struct ScalarPairs {
                 }
             }
         }
-        ScalarPairs<MODE, p + 1>::run(S, wcm, omusq, vtx, vty, vtz, wp, wmn, wall, bottom, is_temp, c, lout, nb, z, Wn,
-                                      act);
+        ScalarPairs<MODE, LEAN, p + 1>::run(S, wcm, omusq, vtx, vty, vtz, wp, wmn, wall, bottom, is_temp, c, lout, nb, la,
+                                            z, Wn, act);
     }
 };
-template <int MODE>
-struct ScalarPairs<MODE, 13> {
+template <int MODE, bool LEAN>
+struct ScalarPairs<MODE, LEAN, 13> {
     static __device__ __forceinline__ void run(const double *, double *, double, double, double, double, double, double,
-                                               bool, bool, bool, const EkConst &, double *, const Nbr &, int, double *,
-                                               bool) {}
+                                               bool, bool, bool, const EkConst &, double *, const Nbr &,
+                                               const LeanAddr &, int, double *, bool) {}
 };
 
-template <int MODE, bool FULL, bool EARR, int NT>
-__device__ __forceinline__ void scalar_role(const StepArgs &a, Sh &sh, const int s, const int lane, const bool act,
-                                            Nbr &nb, const int pi, const int z0, const int z1)
+// one node of a scalar set.  LEAN: deep interior (2 <= z <= NZ-3), see LeanAddr.
+template <int MODE, bool FULL, bool EARR, int NT, bool LEAN>
+__device__ __forceinline__ void scalar_node(const StepArgs &a, Sh &sh, const int s, const int lane, const bool act,
+                                            const int x, const int y, LeanAddr &la, double *W, double *mom_sh,
+                                            const int z)
 {
     const EkConst &c = a.c;
+    Nbr nb;
+    if (!LEAN) set_xy(nb, c, x, y);
     double *lin = a.in[s];
     double *lout = a.out[s];
-    double *W = a.wall + (size_t)(s - 1) * 2 * 27 * c.plane + pi;
     const double wp = c.wp[s], wmn = c.wm[s];
     const bool is_temp = (s == 3);
     const double Ks = s == 1 ? c.K : c.Kn;
-    double *mom_sh = s == 1 ? sh.cp : (s == 2 ? sh.cn : sh.T);
     double S[27];
+    if (LEAN) lean_set_z(la, lin, c, z); else set_z(nb, c, z);
+    const bool bottom = LEAN ? false : (z == 0);
+    const bool wall = LEAN ? false : (bottom || (z == c.NZ - 1));
+    double *Wn = W + (size_t)(bottom ? 0 : 27) * c.plane;
+    if (LEAN) {
+        gather27_lean<MODE>(la, S);
+    } else if (wall) {
+#pragma unroll
+        for (int d = 0; d < 27; ++d) S[d] = Wn[(size_t)d * c.plane];
+    } else {
+        gather27<MODE>(lin, nb, S);
+    }
+    const double m = sum27(S);
+    double E[3] = {0.0, 0.0, 0.0};
+    mom_sh[lane] = m;
+    if (is_temp) {
+        if (LEAN) efield_lean(a, la, z, E); else efield_at<EARR>(a, nb, z, E);
+        sh.E[0][lane] = E[0]; sh.E[1][lane] = E[1]; sh.E[2][lane] = E[2];
+    }
+    if (FULL && act) a.fld[3 + s][nb.fc()] = m;  // charge, chargen, T (LBM.cu:811-813)
+    bar_moments<NT>();
+    // E is read between the two barriers: the temperature warp may only
+    // overwrite it after every warp has passed bar_velocity()
+    if (!is_temp) { E[0] = sh.E[0][lane]; E[1] = sh.E[1][lane]; E[2] = sh.E[2][lane]; }
+    bar_velocity<NT>();
+    double vx = sh.u[0][lane], vy = sh.u[1][lane], vz = sh.u[2][lane];
+    if (!is_temp) {
+        // ion drift u + K*E; Ext does not enter here (LBM.cu:851-862)
+        vx = vx + Ks * E[0];
+        vy = vy + Ks * E[1];
+        vz = vz + Ks * E[2];
+    }
+    double wcm[4] = {c.w[0] * m, c.w[1] * m, c.w[2] * m, c.w[3] * m};
+    const double omusq = 1.0 - 0.5 * (vx * vx + vy * vy + vz * vz) * c.inv_cs2;
+    const double vtx = vx * c.tfac, vty = vy * c.tfac, vtz = vz * c.tfac;
+    // rest population: relaxed in place (LBM.cu:1712-1714); wall rule LBM.cu:2131,2231,2385
+    const double O0 = S[0] - wp * (S[0] - wcm[0] * omusq);
+    if (act) {
+        if (LEAN) (la.b[1] + la.oxy[1][1])[0] = O0;
+        else if (!wall) lout[nb.lc()] = O0;
+        else if (!is_temp) Wn[0] = O0;
+        else if (bottom) Wn[0] = -O0 + c.twoTw[0];
+        else Wn[0] = -O0;
+    }
+    ScalarPairs<MODE, LEAN, 0>::run(S, wcm, omusq, vtx, vty, vtz, wp, wmn, wall, bottom, is_temp, c, lout, nb, la, z, Wn,
+                                    act);
+}
+
+template <int MODE, bool FULL, bool EARR, int NT, bool LEANOK = false>
+__device__ __forceinline__ void scalar_role(const StepArgs &a, Sh &sh, const int s, const int lane, const bool act,
+                                            const int x, const int y, const int pi, const int z0, const int z1)
+{
+    const EkConst &c = a.c;
+    double *W = a.wall + (size_t)(s - 1) * 2 * 27 * c.plane + pi;
+    const bool is_temp = (s == 3);
+    double *mom_sh = s == 1 ? sh.cp : (s == 2 ? sh.cn : sh.T);
+    LeanAddr la;
+    if (LEANOK) {
+        Nbr nb;
+        set_xy(nb, c, x, y);
+        lean_init(la, nb);
+    }
 
     if (z0 == 0) {
         // the bottom wall needs the moments of the z = 1 node first (LBM.cu:663-801)
+        double S[27];
+        Nbr nb;
+        set_xy(nb, c, x, y);
         set_z(nb, c, 1);
-        gather27<MODE>(lin, nb, S);
+        gather27<MODE>(a.in[s], nb, S);
         mom_sh[lane] = sum27(S);
         if (is_temp) {
             double E[3];
@@ -139,63 +209,23 @@ __device__ __forceinline__ void scalar_role(const StepArgs &a, Sh &sh, const int
     }
 
     for (int z = z0; z < z1; ++z) {
-        set_z(nb, c, z);
-        const bool bottom = (z == 0);
-        const bool wall = bottom || (z == c.NZ - 1);
-        double *Wn = W + (size_t)(bottom ? 0 : 27) * c.plane;
-        if (wall) {
-#pragma unroll
-            for (int d = 0; d < 27; ++d) S[d] = Wn[(size_t)d * c.plane];
-        } else {
-            gather27<MODE>(lin, nb, S);
-        }
-        const double m = sum27(S);
-        double E[3] = {0.0, 0.0, 0.0};
-        mom_sh[lane] = m;
-        if (is_temp) {
-            efield_at<EARR>(a, nb, z, E);
-            sh.E[0][lane] = E[0]; sh.E[1][lane] = E[1]; sh.E[2][lane] = E[2];
-        }
-        if (FULL && act) a.fld[3 + s][nb.fc()] = m;  // charge, chargen, T (LBM.cu:811-813)
-        bar_moments<NT>();
-        // E is read between the two barriers: the temperature warp may only
-        // overwrite it after every warp has passed bar_velocity()
-        if (!is_temp) { E[0] = sh.E[0][lane]; E[1] = sh.E[1][lane]; E[2] = sh.E[2][lane]; }
-        bar_velocity<NT>();
-        double vx = sh.u[0][lane], vy = sh.u[1][lane], vz = sh.u[2][lane];
-        if (!is_temp) {
-            // ion drift u + K*E; Ext does not enter here (LBM.cu:851-862)
-            vx = vx + Ks * E[0];
-            vy = vy + Ks * E[1];
-            vz = vz + Ks * E[2];
-        }
-        double wcm[4] = {c.w[0] * m, c.w[1] * m, c.w[2] * m, c.w[3] * m};
-        const double omusq = 1.0 - 0.5 * (vx * vx + vy * vy + vz * vz) * c.inv_cs2;
-        const double vtx = vx * c.tfac, vty = vy * c.tfac, vtz = vz * c.tfac;
-        // rest population: relaxed in place (LBM.cu:1712-1714); wall rule LBM.cu:2131,2231,2385
-        const double O0 = S[0] - wp * (S[0] - wcm[0] * omusq);
-        if (act) {
-            if (!wall) lout[nb.lc()] = O0;
-            else if (!is_temp) Wn[0] = O0;
-            else if (bottom) Wn[0] = -O0 + c.twoTw[0];
-            else Wn[0] = -O0;
-        }
-        ScalarPairs<MODE, 0>::run(S, wcm, omusq, vtx, vty, vtz, wp, wmn, wall, bottom, is_temp, c, lout, nb, z, Wn, act);
+        if (LEANOK && z >= 2 && z < c.NZ - 2) scalar_node<MODE, false, false, NT, true>(a, sh, s, lane, act, x, y, la, W, mom_sh, z);
+        else scalar_node<MODE, FULL, EARR, NT, false>(a, sh, s, lane, act, x, y, la, W, mom_sh, z);
     }
 }
 
 // ---------------------------------------------------------------------------
 // fluid role
 // ---------------------------------------------------------------------------
-template <int MODE, int p>
+template <int MODE, bool LEAN, int p>
 struct FluidPairs {
     static __device__ __forceinline__ void run(const double S[27], double wcr[4], double omusq, const double u[3],
                                                const double F[3], double uF, bool wall, bool top, const EkConst &c,
-                                               double *lout, const Nbr &nb, bool act)
+                                               double *lout, const Nbr &nb, const LeanAddr &la, bool act)
     {
         constexpr int d = 2 * p + 1, o = d + 1, cls = ek_wclass(d);
         double Oa, Ob;
-        if (!wall) {
+        if (LEAN || !wall) {
             const double cu = cdot<d>(u[0], u[1], u[2]);
             const double cF = cdot<d>(F[0], F[1], F[2]);
             const double s_ = cu * c.tfac;
@@ -222,16 +252,17 @@ struct FluidPairs {
             }
         }
         if (act) {
-            put<MODE, d>(lout, nb, Oa);
-            put<MODE, o>(lout, nb, Ob);
+            putx<MODE, d, LEAN>(lout, nb, la, Oa);
+            putx<MODE, o, LEAN>(lout, nb, la, Ob);
         }
-        FluidPairs<MODE, p + 1>::run(S, wcr, omusq, u, F, uF, wall, top, c, lout, nb, act);
+        FluidPairs<MODE, LEAN, p + 1>::run(S, wcr, omusq, u, F, uF, wall, top, c, lout, nb, la, act);
     }
 };
-template <int MODE>
-struct FluidPairs<MODE, 13> {
+template <int MODE, bool LEAN>
+struct FluidPairs<MODE, LEAN, 13> {
     static __device__ __forceinline__ void run(const double *, double *, double, const double *, const double *, double,
-                                               bool, bool, const EkConst &, double *, const Nbr &, bool) {}
+                                               bool, bool, const EkConst &, double *, const Nbr &, const LeanAddr &,
+                                               bool) {}
 };
 
 // momentum expression of LBM.cu:639-644 without the 1/rho factor
@@ -247,19 +278,88 @@ __device__ __forceinline__ void node_force_and_momentum(const EkConst &c, const 
     expr[2] = m[2] * c.cflinv + F[2] * c.dt * 0.5;
 }
 
-template <int MODE, bool FULL, int NT>
-__device__ __forceinline__ void fluid_role(const StepArgs &a, Sh &sh, const int lane, const bool act, Nbr &nb,
-                                           const int z0, const int z1)
+// one node of the fluid set.  LEAN: deep interior (2 <= z <= NZ-3), see LeanAddr.
+template <int MODE, bool FULL, int NT, bool LEAN>
+__device__ __forceinline__ void fluid_node(const StepArgs &a, Sh &sh, const int lane, const bool act, const int x,
+                                           const int y, LeanAddr &la, const double expr1[3], const int z)
 {
     const EkConst &c = a.c;
+    Nbr nb;
+    if (!LEAN) set_xy(nb, c, x, y);
     double *lin = a.in[0];
     double *lout = a.out[0];
     double S[27];
+    const bool top = LEAN ? false : (z == c.NZ - 1);
+    const bool wall = LEAN ? false : ((z == 0) || top);
+    if (LEAN) {
+        lean_set_z(la, lin, c, z);
+        gather27_lean<MODE>(la, S);
+    } else {
+        set_z(nb, c, z);
+        gather27<MODE>(lin, nb, S);
+    }
+    const double rho = sum27(S);
+    double m[3];
+    momentum(S, m);
+    bar_moments<NT>();
+    const double E[3] = {sh.E[0][lane], sh.E[1][lane], sh.E[2][lane]};
+    const double dq = sh.cp[lane] - sh.cn[lane];
+    double F[3], ex_[3], u[3];
+    node_force_and_momentum(c, m, dq, sh.T[lane], E, F, ex_);
+    const double rhoinv = 1.0 / rho;
+    if (!LEAN && z == 0) {
+        // u(z=0) = -(momentum expression of z=1) / rho(z=0)   (LBM.cu:778-800)
+        u[0] = -rhoinv * expr1[0]; u[1] = -rhoinv * expr1[1]; u[2] = -rhoinv * expr1[2];
+    } else {
+        u[0] = rhoinv * ex_[0]; u[1] = rhoinv * ex_[1]; u[2] = rhoinv * ex_[2];
+    }
+    sh.u[0][lane] = u[0]; sh.u[1][lane] = u[1]; sh.u[2][lane] = u[2];
+    bar_velocity<NT>();
+    if (act) {
+        if (LEAN) {
+            a.dq[(size_t)z * c.plane + la.fc] = dq;
+        } else {
+            const int i = nb.fc();
+            a.dq[i] = dq;
+            if (FULL) {  // LBM.cu:807-810
+                a.fld[0][i] = rho; a.fld[1][i] = u[0]; a.fld[2][i] = u[1]; a.fld[3][i] = u[2];
+            }
+        }
+    }
+    double wcr[4] = {c.w[0] * rho, c.w[1] * rho, c.w[2] * rho, c.w[3] * rho};
+    const double omusq = 1.0 - 0.5 * (u[0] * u[0] + u[1] * u[1] + u[2] * u[2]) * c.inv_cs2;
+    const double uF = u[0] * F[0] + u[1] * F[1] + u[2] * F[2];
+    // rest population: TRT + source in the interior, frozen on the walls
+    // (LBM.cu:502-504,1711,1861,1901)
+    double O0 = S[0];
+    if (!wall) O0 = S[0] - c.wp[0] * (S[0] - wcr[0] * omusq) + c.dt * (c.sp * (-c.coe[0] * uF));
+    if (act) {
+        if (LEAN) (la.b[1] + la.oxy[1][1])[0] = O0;
+        else if (MODE == EK_MODE_PUSH) lout[nb.lc()] = O0;
+        else if (!wall) lout[nb.lc()] = O0;
+    }
+    FluidPairs<MODE, LEAN, 0>::run(S, wcr, omusq, u, F, uF, wall, top, c, lout, nb, la, act);
+}
+
+template <int MODE, bool FULL, int NT, bool LEANOK = false>
+__device__ __forceinline__ void fluid_role(const StepArgs &a, Sh &sh, const int lane, const bool act, const int x,
+                                           const int y, const int z0, const int z1)
+{
+    const EkConst &c = a.c;
     double expr1[3] = {0.0, 0.0, 0.0};
+    LeanAddr la;
+    if (LEANOK) {
+        Nbr nb;
+        set_xy(nb, c, x, y);
+        lean_init(la, nb);
+    }
 
     if (z0 == 0) {
+        double S[27];
+        Nbr nb;
+        set_xy(nb, c, x, y);
         set_z(nb, c, 1);
-        gather27<MODE>(lin, nb, S);
+        gather27<MODE>(a.in[0], nb, S);
         double m[3];
         momentum(S, m);
         bar_moments<NT>();
@@ -270,50 +370,13 @@ __device__ __forceinline__ void fluid_role(const StepArgs &a, Sh &sh, const int 
     }
 
     for (int z = z0; z < z1; ++z) {
-        set_z(nb, c, z);
-        const bool top = (z == c.NZ - 1);
-        const bool wall = (z == 0) || top;
-        gather27<MODE>(lin, nb, S);
-        const double rho = sum27(S);
-        double m[3];
-        momentum(S, m);
-        bar_moments<NT>();
-        const double E[3] = {sh.E[0][lane], sh.E[1][lane], sh.E[2][lane]};
-        const double dq = sh.cp[lane] - sh.cn[lane];
-        double F[3], ex_[3], u[3];
-        node_force_and_momentum(c, m, dq, sh.T[lane], E, F, ex_);
-        const double rhoinv = 1.0 / rho;
-        if (z == 0) {
-            // u(z=0) = -(momentum expression of z=1) / rho(z=0)   (LBM.cu:778-800)
-            u[0] = -rhoinv * expr1[0]; u[1] = -rhoinv * expr1[1]; u[2] = -rhoinv * expr1[2];
-        } else {
-            u[0] = rhoinv * ex_[0]; u[1] = rhoinv * ex_[1]; u[2] = rhoinv * ex_[2];
-        }
-        sh.u[0][lane] = u[0]; sh.u[1][lane] = u[1]; sh.u[2][lane] = u[2];
-        bar_velocity<NT>();
-        if (act) {
-            const int i = nb.fc();
-            a.dq[i] = dq;
-            if (FULL) {  // LBM.cu:807-810
-                a.fld[0][i] = rho; a.fld[1][i] = u[0]; a.fld[2][i] = u[1]; a.fld[3][i] = u[2];
-            }
-        }
-        double wcr[4] = {c.w[0] * rho, c.w[1] * rho, c.w[2] * rho, c.w[3] * rho};
-        const double omusq = 1.0 - 0.5 * (u[0] * u[0] + u[1] * u[1] + u[2] * u[2]) * c.inv_cs2;
-        const double uF = u[0] * F[0] + u[1] * F[1] + u[2] * F[2];
-        // rest population: TRT + source in the interior, frozen on the walls
-        // (LBM.cu:502-504,1711,1861,1901)
-        double O0 = S[0];
-        if (!wall) O0 = S[0] - c.wp[0] * (S[0] - wcr[0] * omusq) + c.dt * (c.sp * (-c.coe[0] * uF));
-        if (act) {
-            if (MODE == EK_MODE_PUSH) lout[nb.lc()] = O0;
-            else if (!wall) lout[nb.lc()] = O0;
-        }
-        FluidPairs<MODE, 0>::run(S, wcr, omusq, u, F, uF, wall, top, c, lout, nb, act);
+        if (LEANOK && z >= 2 && z < c.NZ - 2) fluid_node<MODE, false, NT, true>(a, sh, lane, act, x, y, la, expr1, z);
+        else fluid_node<MODE, FULL, NT, false>(a, sh, lane, act, x, y, la, expr1, z);
     }
 }
 
-template <int MODE, bool FULL, bool EARR>
+// LEAN: deep-interior planes take the lean node path (A-A modes only)
+template <int MODE, bool FULL, bool EARR, bool LEAN>
 __global__ void __launch_bounds__(128, 4) ek_step_kernel(const __grid_constant__ StepArgs a)
 {
     __shared__ Sh sh;
@@ -326,11 +389,9 @@ __global__ void __launch_bounds__(128, 4) ek_step_kernel(const __grid_constant__
     const int y = blockIdx.y;
     const int z0 = (blockIdx.z + a.zblock0) * a.zchunk;
     const int z1 = min(z0 + a.zchunk, c.NZ);
-    Nbr nb;
-    set_xy(nb, c, x, y);
     const int pi = y * c.PX + x;
-    if (role == 0) fluid_role<MODE, FULL, 128>(a, sh, lane, act, nb, z0, z1);
-    else scalar_role<MODE, FULL, EARR, 128>(a, sh, role, lane, act, nb, pi, z0, z1);
+    if (role == 0) fluid_role<MODE, FULL, 128, LEAN>(a, sh, lane, act, x, y, z0, z1);
+    else scalar_role<MODE, FULL, EARR, 128, LEAN>(a, sh, role, lane, act, x, y, pi, z0, z1);
 }
 
 // ---------------------------------------------------------------------------
@@ -458,7 +519,7 @@ __global__ void __launch_bounds__(160, 3) ek_step5_kernel(const __grid_constant_
     const int pi = y * c.PX + x;
     if (warp == 0) fluid_half_a<MODE, FULL, 160>(a, sh, lane, act, nb, z0, z1);
     else if (warp == 1) fluid_half_b<MODE, FULL, 160>(a, sh, lane, act, nb, z0, z1);
-    else scalar_role<MODE, FULL, EARR, 160>(a, sh, warp - 1, lane, act, nb, pi, z0, z1);
+    else scalar_role<MODE, FULL, EARR, 160>(a, sh, warp - 1, lane, act, x, y, pi, z0, z1);
 }
 
 // natural-layout export of the pre-collision state (tests, checkpoints)
@@ -501,28 +562,31 @@ cudaError_t launch_mode5(const StepArgs &a, bool full, bool earr, dim3 grid, cud
 }
 
 template <int MODE>
-cudaError_t launch_mode(const StepArgs &a, bool full, bool earr, dim3 grid, cudaStream_t st)
+cudaError_t launch_mode(const StepArgs &a, bool full, bool earr, bool lean, dim3 grid, cudaStream_t st)
 {
+    constexpr bool AA = (MODE != EK_MODE_PUSH);
     if (full) {
-        if (earr) ek_step_kernel<MODE, true, true><<<grid, 128, 0, st>>>(a);
-        else ek_step_kernel<MODE, true, false><<<grid, 128, 0, st>>>(a);
+        if (earr) ek_step_kernel<MODE, true, true, false><<<grid, 128, 0, st>>>(a);
+        else ek_step_kernel<MODE, true, false, false><<<grid, 128, 0, st>>>(a);
     } else {
-        if (earr) ek_step_kernel<MODE, false, true><<<grid, 128, 0, st>>>(a);
-        else ek_step_kernel<MODE, false, false><<<grid, 128, 0, st>>>(a);
+        if (earr) ek_step_kernel<MODE, false, true, false><<<grid, 128, 0, st>>>(a);
+        else if (lean && AA) ek_step_kernel<MODE, false, false, AA><<<grid, 128, 0, st>>>(a);
+        else ek_step_kernel<MODE, false, false, false><<<grid, 128, 0, st>>>(a);
     }
     return cudaGetLastError();
 }
 
 }  // namespace
 
-cudaError_t ek_launch_step(const StepArgs &a, int mode, bool write_fields, bool e_from_arrays, cudaStream_t st)
+cudaError_t ek_launch_step(const StepArgs &a, int mode, bool write_fields, bool e_from_arrays, bool lean,
+                           cudaStream_t st)
 {
     const EkConst &c = a.c;
     dim3 grid((c.NX + 31) / 32, c.NY, a.nzblocks > 0 ? a.nzblocks : (c.NZ + a.zchunk - 1) / a.zchunk);
     switch (mode) {
-    case EK_MODE_AA_EVEN: return launch_mode<EK_MODE_AA_EVEN>(a, write_fields, e_from_arrays, grid, st);
-    case EK_MODE_AA_ODD: return launch_mode<EK_MODE_AA_ODD>(a, write_fields, e_from_arrays, grid, st);
-    default: return launch_mode<EK_MODE_PUSH>(a, write_fields, e_from_arrays, grid, st);
+    case EK_MODE_AA_EVEN: return launch_mode<EK_MODE_AA_EVEN>(a, write_fields, e_from_arrays, lean, grid, st);
+    case EK_MODE_AA_ODD: return launch_mode<EK_MODE_AA_ODD>(a, write_fields, e_from_arrays, lean, grid, st);
+    default: return launch_mode<EK_MODE_PUSH>(a, write_fields, e_from_arrays, false, grid, st);
     }
 }
 

@@ -220,9 +220,10 @@ ek_status ek_poisson_finish(ek_handle *h, int set_walls)
     if (!h) return EK_ERR_INVALID;
     if (!h->allocated) return EK_ERR_STATE;
     DeviceGuard g(h->device);
-    if (set_walls) {
+    if (set_walls || h->phi_walls_dirty) {
         // only needed when something other than the solver touched phi (start-up
         // relaxation, uploads): the solver itself never writes the wall planes
+        h->phi_walls_dirty = false;
         ek_launch_set_walls(h->c, h->fld[EK_PHI], h->stream);
         h->poisson_launches += 1;
         EK_CUDA(h, cudaGetLastError());
@@ -253,6 +254,7 @@ ek_status ek_init_uniform(ek_handle *h)
     ek_status st = ek_alloc_state(h);
     if (st != EK_OK) return st;
     ek_launch_initialization(h->c, h->p, h->fld, h->stream);
+    h->phi_walls_dirty = true;
     EK_CUDA(h, cudaMemcpyAsync(h->phi_old, h->fld[EK_PHI], (size_t)h->c.N * sizeof(double), cudaMemcpyDeviceToDevice,
                                h->stream));
     return EK_OK;
@@ -272,6 +274,7 @@ ek_status ek_pbe_relax(ek_handle *h)
     if (!h || !h->allocated) return EK_ERR_STATE;
     DeviceGuard g(h->device);
     ek_launch_pbe_relax(h->c, h->p.PB_omega, h->fld[EK_PHI], h->phi_old, h->stream);
+    h->phi_walls_dirty = true;
     EK_CUDA(h, cudaGetLastError());
     return EK_OK;
 }

@@ -424,12 +424,13 @@ def test_reference_signature_shim(ek):
 
 
 def test_kernel_variants_agree(ek):
-    """four-, five- and eight-warp step kernels: 0 and 2 chain the sums in the
-    reference's order and must agree bit for bit; 1 adds two partial sums."""
+    """four-, five- and eight-warp step kernels: 0 (lean deep-interior path), 3
+    (general path everywhere) and 2 chain the sums in the reference's order and
+    must agree bit for bit; 1 adds two partial sums."""
     over = dict(NX=40, NY=5, NZ=21, uw=1.0e-4, exf=1.0e6)
     init = synthetic_init(over)
     res = {}
-    for kernel in (0, 1, 2):
+    for kernel in (0, 1, 2, 3):
         for mode in (ek.STREAM_AA, ek.STREAM_PUSH):
             sim = ek.Simulation(ek.default_params(**over), stream_mode=mode, zchunk=6)
             sim.set_option("kernel", kernel)
@@ -439,7 +440,7 @@ def test_kernel_variants_agree(ek):
             res[kernel, mode] = (sim.fields(), np.stack([sim.populations(s) for s in range(4)]))
             sim.close()
     base_f, base_p = res[0, ek.STREAM_AA]
-    for key in ((0, ek.STREAM_PUSH), (2, ek.STREAM_AA), (2, ek.STREAM_PUSH)):
+    for key in ((0, ek.STREAM_PUSH), (2, ek.STREAM_AA), (2, ek.STREAM_PUSH), (3, ek.STREAM_AA), (3, ek.STREAM_PUSH)):
         f, p = res[key]
         for k in util.FIELDS:
             assert np.array_equal(f[k], base_f[k]), (key, k)
