@@ -18,7 +18,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libek_b200.so")
+LIB_PATH = os.environ.get("EK_B200_LIB") or os.path.join(_HERE, "libek_b200.so")  # override: development A/B builds
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "ek_b200.h")
 
 FIELDS = ("rho", "ux", "uy", "uz", "charge", "chargen", "phi", "T", "Ex", "Ey", "Ez")

@@ -107,13 +107,16 @@ void free_state(ek_handle *h)
 
 void collect_events(ek_handle *h)
 {
-    for (auto &e : h->ev_lbm) {
+    for (size_t i = 0; i < h->ev_lbm.size(); ++i) {
+        auto &e = h->ev_lbm[i];
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e.first, e.second);
         h->lbm_ms += ms;
+        h->lbm_ms_mode[h->ev_lbm_mode[i]] += ms;
         cudaEventDestroy(e.first); cudaEventDestroy(e.second);
     }
     h->ev_lbm.clear();
+    h->ev_lbm_mode.clear();
     for (auto &e : h->ev_poi) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e.first, e.second);
@@ -293,10 +296,15 @@ ek_status ek_get_counter(ek_handle *h, const char *key, double *value)
     if (!strcmp(key, "lbm_launches")) { *value = (double)h->lbm_launches; return EK_OK; }
     if (!strcmp(key, "poisson_launches")) { *value = (double)h->poisson_launches; return EK_OK; }
     if (!strcmp(key, "kernel_launches")) { *value = (double)(h->lbm_launches + h->poisson_launches); return EK_OK; }
-    if (!strcmp(key, "lbm_ms") || !strcmp(key, "poisson_ms")) {
+    if (!strncmp(key, "lbm_ms", 6) || !strcmp(key, "poisson_ms")) {
         EK_CUDA(h, cudaStreamSynchronize(h->stream));
         collect_events(h);
-        *value = !strcmp(key, "lbm_ms") ? h->lbm_ms : h->poisson_ms;
+        if (!strcmp(key, "lbm_ms")) *value = h->lbm_ms;
+        else if (!strcmp(key, "lbm_ms_even")) *value = h->lbm_ms_mode[EK_MODE_AA_EVEN];
+        else if (!strcmp(key, "lbm_ms_odd")) *value = h->lbm_ms_mode[EK_MODE_AA_ODD];
+        else if (!strcmp(key, "lbm_ms_push")) *value = h->lbm_ms_mode[EK_MODE_PUSH];
+        else if (!strcmp(key, "poisson_ms")) *value = h->poisson_ms;
+        else return EK_ERR_INVALID;
         return EK_OK;
     }
     return EK_ERR_INVALID;
@@ -310,6 +318,7 @@ ek_status ek_reset_counters(ek_handle *h)
     collect_events(h);
     h->steps = h->lbm_launches = h->poisson_launches = 0;
     h->lbm_ms = h->poisson_ms = 0.0;
+    h->lbm_ms_mode[0] = h->lbm_ms_mode[1] = h->lbm_ms_mode[2] = 0.0;
     return EK_OK;
 }
 
@@ -415,6 +424,7 @@ ek_status ek_stream_collide_save_range(ek_handle *h, int write_fields, int zbloc
     if (h->profile) {
         EK_CUDA(h, cudaEventRecord(e1, h->stream));
         h->ev_lbm.emplace_back(e0, e1);
+        h->ev_lbm_mode.push_back(mode);
     }
     h->lbm_launches += 1;
     if (last) {

@@ -55,6 +55,8 @@ struct ek_handle {
     bool profile = false;
     long long steps = 0, lbm_launches = 0, poisson_launches = 0;
     double lbm_ms = 0.0, poisson_ms = 0.0;
+    double lbm_ms_mode[3] = {0.0, 0.0, 0.0};   // per launch mode (A-A even, A-A odd, push)
+    std::vector<int> ev_lbm_mode;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_lbm, ev_poi;
 };
 

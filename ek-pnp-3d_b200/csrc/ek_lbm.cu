@@ -166,7 +166,7 @@ __device__ __forceinline__ void scalar_node(const StepArgs &a, Sh &sh, const int
     // rest population: relaxed in place (LBM.cu:1712-1714); wall rule LBM.cu:2131,2231,2385
     const double O0 = S[0] - wp * (S[0] - wcm[0] * omusq);
     if (act) {
-        if (LEAN) (la.b[1] + la.oxy[1][1])[0] = O0;
+        if (LEAN) lean_ptr(la.b[1], la.oxy[1][1])[0] = O0;
         else if (!wall) lout[nb.lc()] = O0;
         else if (!is_temp) Wn[0] = O0;
         else if (bottom) Wn[0] = -O0 + c.twoTw[0];
@@ -334,7 +334,7 @@ __device__ __forceinline__ void fluid_node(const StepArgs &a, Sh &sh, const int 
     double O0 = S[0];
     if (!wall) O0 = S[0] - c.wp[0] * (S[0] - wcr[0] * omusq) + c.dt * (c.sp * (-c.coe[0] * uF));
     if (act) {
-        if (LEAN) (la.b[1] + la.oxy[1][1])[0] = O0;
+        if (LEAN) lean_ptr(la.b[1], la.oxy[1][1])[0] = O0;
         else if (MODE == EK_MODE_PUSH) lout[nb.lc()] = O0;
         else if (!wall) lout[nb.lc()] = O0;
     }

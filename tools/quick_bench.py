@@ -42,9 +42,11 @@ def main():
         wall = time.time() - t0
         lbm = sim.counter("lbm_ms") / steps
         poi = sim.counter("poisson_ms") / steps
+        even = sim.counter("lbm_ms_even") / max(1, (steps + 1) // 2)
+        odd = sim.counter("lbm_ms_odd") / max(1, steps // 2)
         cells = NX * NY * NZ
         print(json.dumps({**cfg, "grid": [NX, NY, NZ], "ms_per_step_wall": round(1e3 * wall / steps, 4),
-                          "lbm_ms": round(lbm, 4), "poisson_ms": round(poi, 4),
+                          "lbm_ms": round(lbm, 4), "lbm_even_ms": round(even, 4), "lbm_odd_ms": round(odd, 4), "poisson_ms": round(poi, 4),
                           "mlups_wall": round(cells * steps / wall / 1e6, 1),
                           "lbm_GBps_alg": round(cells * 1744 / (lbm * 1e-3) / 1e9, 1)}), flush=True)
         sim.close()
