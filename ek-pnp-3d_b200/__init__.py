@@ -110,6 +110,14 @@ def load_library():
     for name in ("ek_compute_efield", "ek_init_uniform", "ek_pbe", "ek_pbe_relax", "ek_ensure_allocated",
                  "ek_mark_fields_ready", "ek_refresh_charge_difference", "ek_row_pitch", "ek_lbm_parity"):
         getattr(L, name).argtypes = [H]
+    L.ek_slab_poisson_setup.argtypes = [H, C.c_int]
+    L.ek_slab_poisson_chunks.argtypes = [H]
+    L.ek_slab_poisson_chunk.argtypes = [H, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_void_p),
+                                        C.POINTER(C.c_void_p), C.POINTER(C.c_longlong)]
+    for name in ("ek_slab_poisson_forward", "ek_slab_poisson_gather_x", "ek_slab_poisson_scatter_x",
+                 "ek_slab_poisson_backward"):
+        getattr(L, name).argtypes = [H, C.c_int]
+    L.ek_slab_poisson_solve.argtypes = [H]
     L.ek_adopt_field.argtypes = [H, C.c_int, C.c_void_p]
     L.ek_wall_current.argtypes = [H, C.POINTER(C.c_double)]
     L.ek_max_uz.argtypes = [H, C.POINTER(C.c_double)]

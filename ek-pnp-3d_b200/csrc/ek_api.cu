@@ -102,6 +102,7 @@ void free_state(ek_handle *h)
     cudaFree(h->phi_old); h->phi_old = nullptr;
     cudaFree(h->cp_cols); h->cp_cols = nullptr; h->cp_ky0 = -1; h->cp_kyl = 0;
     ek_poisson_destroy(h->poisson);
+    ek_slab_poisson_destroy(h);
     h->allocated = false;
 }
 

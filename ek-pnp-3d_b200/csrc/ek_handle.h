@@ -38,6 +38,7 @@ struct ek_handle {
     double *dq = nullptr;
     double *phi_old = nullptr;
     EkPoisson poisson;
+    EkSlabPoisson sp;     // distributed solve of the x-slab path
 
     // state machine
     bool fields_ready = false;     // macroscopic arrays hold an initial state

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <cufft.h>
 #include <stdint.h>
+#include <map>
 #include <string>
 
 #include "../../include/ek_b200.h"
@@ -153,7 +154,32 @@ void ek_launch_zfactor_cols(int ncols, int NXg, int NY, int ky0, int M, double L
                             cudaStream_t st);
 void ek_launch_zsolve(int nreal, int ncols, int M, double *x, const double *cp, double scale_dz2, double lift0,
                       double lift1, double norm, double dc_offset, int lift_r, cudaStream_t st);
+void ek_launch_zsolve_rows(int rows, int NXg, int M, double *x, const double *cp, double scale_dz2, double lift0,
+                           double lift1, double norm, double dc_offset, bool has_dc, cudaStream_t st);
 void ek_launch_set_walls(const EkConst &c, double *phi, cudaStream_t st);
+
+// distributed Poisson stage of the x-slab path (ek_slab_poisson.cu)
+#define EK_MAX_RANKS 16
+#define EK_MAX_CHUNKS 16
+struct EkSlabPoisson {
+    bool ready = false;
+    int P = 1, r = 0;                 // ranks, my rank
+    int NXl = 0, NXg = 0, NY = 0, NYH = 0, kyl = 0, M = 0;
+    int K = 1;                        // z-chunks
+    int z0[EK_MAX_CHUNKS + 1] = {};   // chunk bounds (interior-plane index 0..M)
+    int block0[EK_MAX_CHUNKS + 1] = {};  // first LBM z-block of each chunk
+    double *A = nullptr;              // [NY][M][NXl] real: rows for the y-transforms
+    cufftDoubleComplex *S = nullptr;  // send buffers, per chunk [P*kyl][nzc][NXl]
+    cufftDoubleComplex *R = nullptr;  // receive buffers, same shape
+    cufftDoubleComplex *X = nullptr;  // full-x pencils [kyl][M][NXg]
+    double *cp = nullptr;             // LU factors of my columns [M][kyl*NXg]
+    std::map<int, cufftHandle> plan_yf, plan_yb;  // y-transforms per chunk height
+    cufftHandle plan_x = 0;
+    bool plan_x_ok = false;
+    cufftDoubleComplex *peerX[EK_MAX_RANKS] = {};  // direct peer-memory transport (optional)
+    cufftDoubleComplex *peerR[EK_MAX_RANKS] = {};
+};
+void ek_slab_poisson_destroy(ek_handle *h);
 
 // ---------------------------------------------------------------------------
 // LBM stage (ek_lbm.cu) and start-up kernels (ek_init.cu)

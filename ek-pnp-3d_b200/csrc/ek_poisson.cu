@@ -114,15 +114,21 @@ __global__ void k_zfactor(int ncols, int NXH, int M, const double *__restrict__ 
 //   d_j  = dz^2 * ( -(F/eps) * dq^_j  -  [j=0] V0/dz^2 * NXY  -  [j=M-1] V1/dz^2 * NXY )   (lift: (0,0) column only)
 //   d'_j = (d_j - d'_{j-1}) c'_j ;   phi^_j = d'_j - c'_j phi^_{j+1}
 // The result is scaled by 1/(NX*NY) for cuFFT's unnormalised inverse.
+// Layout: x[blockIdx.y * x_outer + j * xj + r], cp[j * ncols + blockIdx.y * cp_outer + (r >> 1)]: blockIdx.y = 0
+// and xj = nreal for the single-GPU half spectrum [j][ky][kx]; blockIdx.y = local ky row and xj = 2*NXg for
+// the distributed solve's pencils [ky][j][kx] (ek_slab_poisson.cu).
 template <int UNROLL>
 __global__ void __launch_bounds__(128) k_zsolve(int nreal, int ncols, int M, double *__restrict__ x,
                                                 const double *__restrict__ cp, double scale_dz2, double lift0,
-                                                double lift1, double norm, double dc_offset, int lift_r)
+                                                double lift1, double norm, double dc_offset, int lift_r,
+                                                long long xj, long long x_outer, int cp_outer)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nreal) return;
-    const int col = r >> 1;
-    const bool lifted = (r == lift_r);  // real part of the (kx,ky) = (0,0) column (-1: not in this set of columns)
+    const int col = blockIdx.y * cp_outer + (r >> 1);
+    x += (size_t)blockIdx.y * x_outer;
+    // real part of the (kx,ky) = (0,0) column (lift_r = -1: not in this set of columns)
+    const bool lifted = (r == lift_r && blockIdx.y == 0);
     double prev = 0.0;
     int j = 0;
     // forward elimination; loads are independent of the recurrence, so a block
@@ -131,7 +137,7 @@ __global__ void __launch_bounds__(128) k_zsolve(int nreal, int ncols, int M, dou
         double g[UNROLL], c[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            g[u] = x[(size_t)(j + u) * nreal + r];
+            g[u] = x[(size_t)(j + u) * xj + r];
             c[u] = cp[(size_t)(j + u) * ncols + col];
         }
 #pragma unroll
@@ -142,39 +148,39 @@ __global__ void __launch_bounds__(128) k_zsolve(int nreal, int ncols, int M, dou
                 if (j + u == M - 1) d += lift1;
             }
             prev = (d - prev) * c[u];
-            x[(size_t)(j + u) * nreal + r] = prev;
+            x[(size_t)(j + u) * xj + r] = prev;
         }
     }
     for (; j < M; ++j) {
-        double d = scale_dz2 * x[(size_t)j * nreal + r];
+        double d = scale_dz2 * x[(size_t)j * xj + r];
         if (lifted) {
             if (j == 0) d += lift0;
             if (j == M - 1) d += lift1;
         }
         prev = (d - prev) * cp[(size_t)j * ncols + col];
-        x[(size_t)j * nreal + r] = prev;
+        x[(size_t)j * xj + r] = prev;
     }
     // back substitution
     const double off = lifted ? dc_offset : 0.0;
     double phi = prev;
-    x[(size_t)(M - 1) * nreal + r] = phi * norm + off;
+    x[(size_t)(M - 1) * xj + r] = phi * norm + off;
     j = M - 2;
     for (; j - UNROLL + 1 >= 0; j -= UNROLL) {
         double g[UNROLL], c[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            g[u] = x[(size_t)(j - u) * nreal + r];
+            g[u] = x[(size_t)(j - u) * xj + r];
             c[u] = cp[(size_t)(j - u) * ncols + col];
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             phi = g[u] - c[u] * phi;
-            x[(size_t)(j - u) * nreal + r] = phi * norm + off;
+            x[(size_t)(j - u) * xj + r] = phi * norm + off;
         }
     }
     for (; j >= 0; --j) {
-        phi = x[(size_t)j * nreal + r] - cp[(size_t)j * ncols + col] * phi;
-        x[(size_t)j * nreal + r] = phi * norm + off;
+        phi = x[(size_t)j * xj + r] - cp[(size_t)j * ncols + col] * phi;
+        x[(size_t)j * xj + r] = phi * norm + off;
     }
 }
 
@@ -274,7 +280,17 @@ void ek_launch_zsolve(int nreal, int ncols, int M, double *x, const double *cp, 
                       double lift1, double norm, double dc_offset, int lift_r, cudaStream_t st)
 {
     k_zsolve<8><<<(nreal + 127) / 128, 128, 0, st>>>(nreal, ncols, M, x, cp, scale_dz2, lift0, lift1, norm, dc_offset,
-                                                       lift_r);
+                                                       lift_r, nreal, 0, 0);
+}
+
+// pencils x[ky][j][kx] complex (rows local ky rows, NXg complex per row); cp[j][rows*NXg]
+void ek_launch_zsolve_rows(int rows, int NXg, int M, double *x, const double *cp, double scale_dz2, double lift0,
+                           double lift1, double norm, double dc_offset, bool has_dc, cudaStream_t st)
+{
+    const int nreal = 2 * NXg;
+    dim3 grid((nreal + 127) / 128, rows);
+    k_zsolve<8><<<grid, 128, 0, st>>>(nreal, rows * NXg, M, x, cp, scale_dz2, lift0, lift1, norm, dc_offset,
+                                        has_dc ? 0 : -1, (long long)nreal, (long long)M * nreal, NXg);
 }
 
 void ek_launch_set_walls(const EkConst &c, double *phi, cudaStream_t st)
@@ -339,7 +355,7 @@ ek_status ek_poisson_solve(ek_handle *h, EkPoisson &P, const ek_params &p, const
         const double off = dc_mode == EK_DC_PRESCRIBED ? -dc_ghat0 / size : 0.0;
         k_zsolve<8><<<(nreal + 127) / 128, 128, 0, st>>>(nreal, ncols, M, reinterpret_cast<double *>(P.spec2), P.cp,
                                                            -(c.CtoC / c.eps) * c.dz * c.dz, -c.voltage * nxy,
-                                                           -c.voltage2 * nxy, 1.0 / nxy, off, 0);
+                                                           -c.voltage2 * nxy, 1.0 / nxy, off, 0, nreal, 0, 0);
         EK_CUFFT(h, cufftExecZ2D(P.plan2_inv, P.spec2, phi + c.plane));
         k_set_walls<<<dim3((c.NX + 127) / 128, c.NY), b, 0, st>>>(c, phi);
         n = 2;

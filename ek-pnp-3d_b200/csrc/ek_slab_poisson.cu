@@ -1,0 +1,302 @@
+// ek_slab_poisson.cu -- the distributed fast_Poisson() of the x-slab path
+// (replaces poisson.cu:75-103 on a domain split along x).
+//
+// The linear system is the one of ek_poisson.cu path 0: Fourier in the periodic
+// x and y, second differences in z between the Dirichlet walls.  x is split over
+// the ranks, so the x-transform sits between two slab transposes:
+//
+//   c+ - c-  [z][y][x_local]
+//     k_planes_to_rows   -> A  [y][z][x_local]            (hand-written, one pass)
+//     cuFFT D2Z along y  -> S  [ky][z][x_local]           (strided batch, no packing pass:
+//                                                          rows of S are already grouped by the
+//                                                          destination rank of the transpose)
+//     transpose 1: all-to-all over the ky blocks  (host: NCCL; or direct peer writes)
+//     k_copy_rows        -> X  [ky_local][z][x_global]    (hand-written)
+//     cuFFT Z2Z along x, in place
+//     k_zsolve           tridiagonal z-system of every (ky,kx) column, in place
+//     cuFFT Z2Z inverse along x, in place
+//     k_copy_rows        -> S  [rank][ky_local][z][x_local]
+//     transpose 2: all-to-all back                -> R = [ky][z][x_local]
+//     cuFFT Z2D along y  -> A  [y][z][x_local]
+//     k_rows_to_planes   -> phi [z][y][x_local]           (hand-written)
+//
+// Everything is chunked along z (the chunks are groups of the LBM kernel's
+// z-blocks), so that the host can start the forward half of chunk c as soon as
+// the LBM launch that produces its planes has finished, and so that the
+// all-to-all of one chunk travels while the next one is transformed.
+// cuFFT does the transforms only; packing, the eigen-solve and unpacking are
+// the kernels of this file and k_zsolve (ek_poisson.cu).
+#include <string.h>
+
+#include "ek_handle.h"
+
+namespace {
+
+// A[(y*M + zi)*NXl + x] = dq[(zi+1)*plane + y*PX + x]   for zi in [za, zb)
+__global__ void k_planes_to_rows(int NXl, int NY, int M, int PX, long long plane, int za,
+                                 const double *__restrict__ dq, double *__restrict__ A)
+{
+    const int x2 = blockIdx.x * blockDim.x + threadIdx.x;  // pairs of columns (NXl and PX are even)
+    if (2 * x2 >= NXl) return;
+    const int y = blockIdx.y, zi = za + blockIdx.z;
+    const double2 v = *reinterpret_cast<const double2 *>(dq + (size_t)(zi + 1) * plane + (size_t)y * PX + 2 * x2);
+    *reinterpret_cast<double2 *>(A + ((size_t)y * M + zi) * NXl + 2 * x2) = v;
+}
+
+// phi[(zi+1)*plane + y*PX + x] = A[(y*M + zi)*NXl + x]   for zi in [za, zb)
+__global__ void k_rows_to_planes(int NXl, int NY, int M, int PX, long long plane, int za,
+                                 const double *__restrict__ A, double *__restrict__ phi)
+{
+    const int x2 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (2 * x2 >= NXl) return;
+    const int y = blockIdx.y, zi = za + blockIdx.z;
+    const double2 v = *reinterpret_cast<const double2 *>(A + ((size_t)y * M + zi) * NXl + 2 * x2);
+    *reinterpret_cast<double2 *>(phi + (size_t)(zi + 1) * plane + (size_t)y * PX + 2 * x2) = v;
+}
+
+// The two re-blockings around the transposes are copies of rows of NXl complex
+// numbers between a [rank][ky_local][z][x_local] buffer and the full-x pencils
+// X[ky_local][z][x_global]: row (i, ky, zi) <-> X[ky][z0+zi][i*NXl ...].  src/dst
+// are per-rank base pointers, so the same kernel serves the NCCL transport
+// (local buffers) and direct peer-memory writes.
+struct RowPtrs {
+    const double2 *src[EK_MAX_RANKS];
+    double2 *dst[EK_MAX_RANKS];
+};
+
+__global__ void k_copy_rows(RowPtrs p, int rowlen, int nz, long long src_ky, long long src_z, long long dst_ky,
+                            long long dst_z)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= rowlen) return;
+    const int ky = blockIdx.y / nz, zi = blockIdx.y % nz, i = blockIdx.z;
+    p.dst[i][(size_t)ky * dst_ky + (size_t)zi * dst_z + x] = p.src[i][(size_t)ky * src_ky + (size_t)zi * src_z + x];
+}
+
+ek_status plan_for(ek_handle *h, std::map<int, cufftHandle> &plans, int nzc, bool forward)
+{
+    if (plans.count(nzc)) return EK_OK;
+    EkSlabPoisson &S = h->sp;
+    cufftHandle plan;
+    int n[1] = {S.NY};
+    int emb[1] = {S.NY};
+    if (forward) {
+        // in: A + za*NXl, element (y; b) at y*(M*NXl) + b;  out: chunk buffer, (ky; b) at ky*(nzc*NXl) + b
+        EK_CUFFT(h, cufftPlanMany(&plan, 1, n, emb, S.M * S.NXl, 1, emb, nzc * S.NXl, 1, CUFFT_D2Z, nzc * S.NXl));
+    } else {
+        EK_CUFFT(h, cufftPlanMany(&plan, 1, n, emb, nzc * S.NXl, 1, emb, S.M * S.NXl, 1, CUFFT_Z2D, nzc * S.NXl));
+    }
+    plans[nzc] = plan;
+    return EK_OK;
+}
+
+}  // namespace
+
+void ek_slab_poisson_destroy(ek_handle *h)
+{
+    EkSlabPoisson &S = h->sp;
+    for (auto &kv : S.plan_yf) cufftDestroy(kv.second);
+    for (auto &kv : S.plan_yb) cufftDestroy(kv.second);
+    S.plan_yf.clear();
+    S.plan_yb.clear();
+    if (S.plan_x_ok) cufftDestroy(S.plan_x);
+    S.plan_x_ok = false;
+    cudaFree(S.A); cudaFree(S.S); cudaFree(S.R); cudaFree(S.X); cudaFree(S.cp);
+    S.A = nullptr; S.S = S.R = S.X = nullptr; S.cp = nullptr;
+    S.ready = false;
+}
+
+extern "C" {
+
+// nchunks groups of the LBM z-blocks ("zchunk" planes each) define the chunks.
+ek_status ek_slab_poisson_setup(ek_handle *h, int nchunks)
+{
+    if (!h || !h->slab) return EK_ERR_STATE;
+    if (h->nranks > EK_MAX_RANKS) { ek_set_error(h, "too many ranks"); return EK_ERR_INVALID; }
+    DeviceGuard g(h->device);
+    ek_status st = ek_alloc_state(h);
+    if (st != EK_OK) return st;
+    ek_slab_poisson_destroy(h);
+    EkSlabPoisson &S = h->sp;
+    const EkConst &c = h->c;
+    if (c.NX % 2) { ek_set_error(h, "the slab width must be even"); return EK_ERR_INVALID; }
+    S.P = h->nranks; S.r = h->rank;
+    S.NXl = c.NX; S.NXg = h->NXg; S.NY = c.NY; S.NYH = c.NY / 2 + 1; S.M = c.NZ - 2;
+    S.kyl = (S.NYH + S.P - 1) / S.P;
+    const int nblocks = (c.NZ + h->zchunk - 1) / h->zchunk;
+    S.K = nchunks < 1 ? 1 : (nchunks > nblocks ? nblocks : nchunks);
+    if (S.K > EK_MAX_CHUNKS) S.K = EK_MAX_CHUNKS;
+    for (int k = 0; k <= S.K; ++k) {
+        const int b = (int)((long long)nblocks * k / S.K);     // first LBM z-block of chunk k
+        int z = b * h->zchunk;                                   // first plane
+        if (z > c.NZ) z = c.NZ;
+        S.block0[k] = b;
+        // interior-plane index zi = z - 1, clipped to [0, M]
+        int zi = z - 1;
+        if (zi < 0) zi = 0;
+        if (zi > S.M) zi = S.M;
+        if (k == S.K) zi = S.M;
+        S.z0[k] = zi;
+    }
+    const size_t nreal = (size_t)S.NY * S.M * S.NXl;
+    const size_t nspec = (size_t)S.P * S.kyl * S.M * S.NXl;
+    const size_t npen = (size_t)S.kyl * S.M * S.NXg;
+    EK_CUDA(h, cudaMalloc((void **)&S.A, nreal * sizeof(double)));
+    EK_CUDA(h, cudaMalloc((void **)&S.S, nspec * sizeof(cufftDoubleComplex)));
+    EK_CUDA(h, cudaMalloc((void **)&S.R, nspec * sizeof(cufftDoubleComplex)));
+    EK_CUDA(h, cudaMalloc((void **)&S.X, npen * sizeof(cufftDoubleComplex)));
+    // rows ky >= NY/2+1 of the last rank's block are padding: keep them zero
+    EK_CUDA(h, cudaMemsetAsync(S.S, 0, nspec * sizeof(cufftDoubleComplex), h->stream));
+    EK_CUDA(h, cudaMemsetAsync(S.R, 0, nspec * sizeof(cufftDoubleComplex), h->stream));
+    EK_CUDA(h, cudaMemsetAsync(S.X, 0, npen * sizeof(cufftDoubleComplex), h->stream));
+    for (int k = 0; k < S.K; ++k) {
+        const int nzc = S.z0[k + 1] - S.z0[k];
+        if (nzc <= 0) continue;
+        st = plan_for(h, S.plan_yf, nzc, true);
+        if (st != EK_OK) return st;
+        st = plan_for(h, S.plan_yb, nzc, false);
+        if (st != EK_OK) return st;
+    }
+    {
+        int n[1] = {S.NXg};
+        EK_CUFFT(h, cufftPlanMany(&S.plan_x, 1, n, nullptr, 1, S.NXg, nullptr, 1, S.NXg, CUFFT_Z2Z, S.kyl * S.M));
+        S.plan_x_ok = true;
+    }
+    // LU factors of the z-operator of my (ky, kx) columns
+    const int ncols = S.kyl * S.NXg;
+    EK_CUDA(h, cudaMalloc((void **)&S.cp, (size_t)S.M * ncols * sizeof(double)));
+    ek_launch_zfactor_cols(ncols, S.NXg, c.NY, S.r * S.kyl, S.M, h->p.Lx, h->p.Ly, c.dz, S.cp, h->stream);
+    EK_CUDA(h, cudaGetLastError());
+    for (int i = 0; i < EK_MAX_RANKS; ++i) { S.peerX[i] = nullptr; S.peerR[i] = nullptr; }
+    S.peerX[S.r] = S.X;
+    S.peerR[S.r] = S.R;
+    S.ready = true;
+    return EK_OK;
+}
+
+int ek_slab_poisson_chunks(ek_handle *h) { return (h && h->sp.ready) ? h->sp.K : 0; }
+
+// chunk k: the LBM z-blocks [block0, block1) produce its planes; `send`/`recv`
+// are its transpose buffers, `count` complex numbers each (nranks equal parts)
+ek_status ek_slab_poisson_chunk(ek_handle *h, int k, int *block0, int *block1, void **send, void **recv,
+                                long long *count)
+{
+    if (!h || !h->sp.ready || k < 0 || k >= h->sp.K) return EK_ERR_INVALID;
+    EkSlabPoisson &S = h->sp;
+    const size_t off = (size_t)S.P * S.kyl * S.z0[k] * S.NXl;
+    if (block0) *block0 = S.block0[k];
+    if (block1) *block1 = S.block0[k + 1];
+    if (send) *send = S.S + off;
+    if (recv) *recv = S.R + off;
+    if (count) *count = (long long)S.P * S.kyl * (S.z0[k + 1] - S.z0[k]) * S.NXl;
+    return EK_OK;
+}
+
+// c+ - c- of the planes of chunk k -> y-spectrum in the chunk's send buffer
+ek_status ek_slab_poisson_forward(ek_handle *h, int k)
+{
+    if (!h || !h->sp.ready || k < 0 || k >= h->sp.K) return EK_ERR_INVALID;
+    DeviceGuard g(h->device);
+    EkSlabPoisson &S = h->sp;
+    const EkConst &c = h->c;
+    const int za = S.z0[k], nzc = S.z0[k + 1] - za;
+    if (nzc <= 0) return EK_OK;
+    dim3 b(128), gr((S.NXl / 2 + 127) / 128, S.NY, nzc);
+    k_planes_to_rows<<<gr, b, 0, h->stream>>>(S.NXl, S.NY, S.M, c.PX, c.plane, za, h->dq, S.A);
+    EK_CUDA(h, cudaGetLastError());
+    cufftHandle plan = S.plan_yf[nzc];
+    cufftDoubleComplex *out = S.S + (size_t)S.P * S.kyl * za * S.NXl;
+    // rows ky >= NY/2+1 (padding of the last rank's block) are not written by the transform
+    if (S.P * S.kyl > S.NYH)
+        EK_CUDA(h, cudaMemsetAsync(out + (size_t)S.NYH * nzc * S.NXl, 0,
+                                   (size_t)(S.P * S.kyl - S.NYH) * nzc * S.NXl * sizeof(cufftDoubleComplex), h->stream));
+    EK_CUFFT(h, cufftSetStream(plan, h->stream));
+    EK_CUFFT(h, cufftExecD2Z(plan, S.A + (size_t)za * S.NXl, out));
+    h->poisson_launches += 1;
+    return EK_OK;
+}
+
+// after transpose 1 of chunk k: received ky blocks -> full-x pencils
+ek_status ek_slab_poisson_gather_x(ek_handle *h, int k)
+{
+    if (!h || !h->sp.ready || k < 0 || k >= h->sp.K) return EK_ERR_INVALID;
+    DeviceGuard g(h->device);
+    EkSlabPoisson &S = h->sp;
+    const int za = S.z0[k], nzc = S.z0[k + 1] - za;
+    if (nzc <= 0) return EK_OK;
+    RowPtrs p;
+    const double2 *R = reinterpret_cast<const double2 *>(S.R) + (size_t)S.P * S.kyl * za * S.NXl;
+    double2 *X = reinterpret_cast<double2 *>(S.X);
+    for (int i = 0; i < S.P; ++i) {
+        p.src[i] = R + (size_t)i * S.kyl * nzc * S.NXl;                // what rank i sent: [kyl][nzc][NXl]
+        p.dst[i] = X + (size_t)za * S.NXg + (size_t)i * S.NXl;         // its columns of my pencils
+    }
+    dim3 b(128), gr((S.NXl + 127) / 128, S.kyl * nzc, S.P);
+    k_copy_rows<<<gr, b, 0, h->stream>>>(p, S.NXl, nzc, (long long)nzc * S.NXl, S.NXl, (long long)S.M * S.NXg, S.NXg);
+    EK_CUDA(h, cudaGetLastError());
+    h->poisson_launches += 1;
+    return EK_OK;
+}
+
+// x-transform, z-solve, inverse x-transform of my ky rows (all chunks present)
+ek_status ek_slab_poisson_solve(ek_handle *h)
+{
+    if (!h || !h->sp.ready) return EK_ERR_INVALID;
+    DeviceGuard g(h->device);
+    EkSlabPoisson &S = h->sp;
+    const EkConst &c = h->c;
+    EK_CUFFT(h, cufftSetStream(S.plan_x, h->stream));
+    EK_CUFFT(h, cufftExecZ2Z(S.plan_x, S.X, S.X, CUFFT_FORWARD));
+    const double nxy = (double)S.NXg * (double)c.NY;
+    const double size = (double)((unsigned int)S.NXg * (unsigned int)c.NY * (unsigned int)(2 * (c.NZ - 1)));
+    const double off = h->dc_mode == EK_DC_PRESCRIBED ? -h->dc_ghat0 / size : 0.0;
+    ek_launch_zsolve_rows(S.kyl, S.NXg, S.M, reinterpret_cast<double *>(S.X), S.cp, -(c.CtoC / c.eps) * c.dz * c.dz,
+                          -c.voltage * nxy, -c.voltage2 * nxy, 1.0 / nxy, off, S.r == 0, h->stream);
+    EK_CUDA(h, cudaGetLastError());
+    EK_CUFFT(h, cufftExecZ2Z(S.plan_x, S.X, S.X, CUFFT_INVERSE));
+    h->poisson_launches += 1;
+    return EK_OK;
+}
+
+// before transpose 2 of chunk k: pencils -> per-rank x blocks in the send buffer
+ek_status ek_slab_poisson_scatter_x(ek_handle *h, int k)
+{
+    if (!h || !h->sp.ready || k < 0 || k >= h->sp.K) return EK_ERR_INVALID;
+    DeviceGuard g(h->device);
+    EkSlabPoisson &S = h->sp;
+    const int za = S.z0[k], nzc = S.z0[k + 1] - za;
+    if (nzc <= 0) return EK_OK;
+    RowPtrs p;
+    double2 *Sd = reinterpret_cast<double2 *>(S.S) + (size_t)S.P * S.kyl * za * S.NXl;
+    const double2 *X = reinterpret_cast<const double2 *>(S.X);
+    for (int i = 0; i < S.P; ++i) {
+        p.src[i] = X + (size_t)za * S.NXg + (size_t)i * S.NXl;
+        p.dst[i] = Sd + (size_t)i * S.kyl * nzc * S.NXl;
+    }
+    dim3 b(128), gr((S.NXl + 127) / 128, S.kyl * nzc, S.P);
+    k_copy_rows<<<gr, b, 0, h->stream>>>(p, S.NXl, nzc, (long long)S.M * S.NXg, S.NXg, (long long)nzc * S.NXl, S.NXl);
+    EK_CUDA(h, cudaGetLastError());
+    h->poisson_launches += 1;
+    return EK_OK;
+}
+
+// after transpose 2 of chunk k: inverse y-transform -> interior planes of phi
+ek_status ek_slab_poisson_backward(ek_handle *h, int k)
+{
+    if (!h || !h->sp.ready || k < 0 || k >= h->sp.K) return EK_ERR_INVALID;
+    DeviceGuard g(h->device);
+    EkSlabPoisson &S = h->sp;
+    const EkConst &c = h->c;
+    const int za = S.z0[k], nzc = S.z0[k + 1] - za;
+    if (nzc <= 0) return EK_OK;
+    cufftHandle plan = S.plan_yb[nzc];
+    EK_CUFFT(h, cufftSetStream(plan, h->stream));
+    EK_CUFFT(h, cufftExecZ2D(plan, S.R + (size_t)S.P * S.kyl * za * S.NXl, S.A + (size_t)za * S.NXl));
+    dim3 b(128), gr((S.NXl / 2 + 127) / 128, S.NY, nzc);
+    k_rows_to_planes<<<gr, b, 0, h->stream>>>(S.NXl, S.NY, S.M, c.PX, c.plane, za, S.A, h->fld[EK_PHI]);
+    EK_CUDA(h, cudaGetLastError());
+    h->poisson_launches += 1;
+    return EK_OK;
+}
+
+}  // extern "C"

@@ -8,10 +8,13 @@ csrc/ek_slab.cu:
     each set travel to the two x-neighbours (phase A after an even A-A step,
     phase B after an odd one) -- NCCL send/recv between ring neighbours;
   * phi halo: one column per face for the fused E = -grad(phi);
-  * Poisson: local real FFT along y, all-to-all transpose to full-x pencils,
-    complex FFT along x, the hand-written z-solve (ek_zsolve_columns), and back.
-    The transforms are cuFFT (through torch.fft); the transposes are NCCL
-    all-to-alls.
+  * Poisson: the native stage of csrc/ek_slab_poisson.cu (cuFFT transforms,
+    hand-written re-blocking and z-solve kernels) chunked along z; this module
+    only moves the chunk buffers between ranks (NCCL all-to-all) and pipelines
+    chunk k's forward half against the LBM launch of chunk k+1.
+    The torch.fft functions below (y_forward ... y_backward) restate the same
+    algebra device-independently; they are the CPU tests' model of the stage
+    (tests/test_slab_cpu.py, gloo), not the product path.
 
 `Comm` abstracts the transport: `DistComm` is torch.distributed (NCCL, one
 slab per process); `LocalComm` keeps all slabs of a group in ONE process on one
@@ -38,8 +41,8 @@ class _DevArray:
                                          "version": 2, "strides": None}
 
 
-def device_view(ptr: int, shape, device) -> torch.Tensor:
-    return torch.as_tensor(_DevArray(ptr, shape), device=device)
+def device_view(ptr: int, shape, device, dtype="<f8") -> torch.Tensor:
+    return torch.as_tensor(_DevArray(ptr, shape, dtype), device=device)
 
 
 def partition(NX: int, nranks: int):
@@ -112,9 +115,14 @@ class LocalComm:
     def neighbor_exchange_finish(self, handle):
         pass
 
-    def all_to_all_start(self, send):
+    def all_to_all_start(self, send, recv=None):
         P = self.nranks
-        return [torch.stack([send[p][r] for p in range(P)]) for r in range(P)]
+        if recv is None:
+            return [torch.stack([send[p][r] for p in range(P)]) for r in range(P)]
+        for r in range(P):
+            for p in range(P):
+                recv[r][p].copy_(send[p][r])
+        return recv
 
     def all_to_all_finish(self, handle):
         return handle
@@ -155,8 +163,8 @@ class DistComm:
         for req in handle:
             req.wait()
 
-    def all_to_all_start(self, send):
-        recv = torch.empty_like(send[0])
+    def all_to_all_start(self, send, recv=None):
+        recv = torch.empty_like(send[0]) if recv is None else recv[0]
         if self.nranks == 1:
             recv.copy_(send[0])
             return (None, recv)
@@ -184,8 +192,8 @@ def _blocking(comm):
     def neighbor_exchange(to_left, to_right, from_left, from_right):
         comm.neighbor_exchange_finish(comm.neighbor_exchange_start(to_left, to_right, from_left, from_right))
 
-    def all_to_all(send):
-        return comm.all_to_all_finish(comm.all_to_all_start(send))
+    def all_to_all(send, recv=None):
+        return comm.all_to_all_finish(comm.all_to_all_start(send, recv))
     comm.neighbor_exchange = neighbor_exchange
     comm.all_to_all = all_to_all
     return comm
@@ -219,33 +227,44 @@ class Slab:
         np_ = self.NY * self.NZ
         self.p_to_l, self.p_to_r, self.p_from_l, self.p_from_r = mk(np_), mk(np_), mk(np_), mk(np_)
         self.nyh, self.kyl = ky_chunks(self.NY, nranks)
+        self.send, self.recv, self.blocks = [], [], []
+
+    def setup_poisson(self, nchunks: int):
+        """native distributed Poisson stage: chunk buffers as torch views for the transport"""
+        self.ck(self.L.ek_slab_poisson_setup(self.h, int(nchunks)), "ek_slab_poisson_setup")
+        K = self.L.ek_slab_poisson_chunks(self.h)
+        self.send, self.recv, self.blocks = [], [], []
+        for k in range(K):
+            b0, b1, cnt = C.c_int(), C.c_int(), C.c_longlong()
+            ps, pr = C.c_void_p(), C.c_void_p()
+            self.ck(self.L.ek_slab_poisson_chunk(self.h, k, C.byref(b0), C.byref(b1), C.byref(ps), C.byref(pr),
+                                                 C.byref(cnt)), "ek_slab_poisson_chunk")
+            n = cnt.value // self.nranks
+            self.blocks.append((b0.value, b1.value))
+            if cnt.value == 0:
+                self.send.append(None)
+                self.recv.append(None)
+                continue
+            self.send.append(device_view(ps.value, (self.nranks, n), self.dev, "<c16"))
+            self.recv.append(device_view(pr.value, (self.nranks, n), self.dev, "<c16"))
+        return K
 
     def ck(self, st, what):
         self.sim._ck(st, what)
 
-    # -- Poisson pieces --------------------------------------------------------
-    def poisson_forward_local(self, z0: int = 0, z1: int | None = None) -> torch.Tensor:
-        """real FFT along y of interior planes [z0, z1), split by ky chunk: (P, z1-z0, kyl, NX) complex"""
-        z1 = self.M if z1 is None else z1
-        return y_forward(self.dq[1 + z0:1 + z1, :, :self.NX], self.nranks, self.kyl)
+    # -- Poisson pieces, torch.fft restatement (cross-check of the native stage in the GPU tests) ----
+    def poisson_forward_local(self) -> torch.Tensor:
+        return y_forward(self.dq[1:1 + self.M, :, :self.NX], self.nranks, self.kyl)
 
     def poisson_middle(self, recv: torch.Tensor) -> torch.Tensor:
-        """recv (P, M, kyl, NXl): my ky chunk, every rank's x block -> x FFT, z-solve, back"""
         X = x_forward(recv)
         self.ck(self.L.ek_zsolve_columns(self.h, C.c_void_p(X.data_ptr()), self.rank * self.kyl, self.kyl),
                 "ek_zsolve_columns")
         return x_backward(X, self.nranks)
 
-    def poisson_backward_local(self, recv: torch.Tensor, z0: int = 0, z1: int | None = None, last: bool = True):
-        """recv (P, z1-z0, kyl, NX): every ky chunk of my x block -> inverse real FFT along y -> phi"""
-        z1 = self.M if z1 is None else z1
-        self.phi[1 + z0:1 + z1, :, :self.NX] = y_backward(recv, self.NY)
-        if last:
-            self.ck(self.L.ek_poisson_finish(self.h, 0), "ek_poisson_finish")
-
-    def zsolve(self, X: torch.Tensor):
-        self.ck(self.L.ek_zsolve_columns(self.h, C.c_void_p(X.data_ptr()), self.rank * self.kyl, self.kyl),
-                "ek_zsolve_columns")
+    def poisson_backward_local(self, recv: torch.Tensor):
+        self.phi[1:1 + self.M, :, :self.NX] = y_backward(recv, self.NY)
+        self.ck(self.L.ek_poisson_finish(self.h, 0), "ek_poisson_finish")
 
 
 # ---------------------------------------------------------------------------
@@ -257,9 +276,18 @@ class SlabGroup:
         self.nranks = comm.nranks
         self.slabs = [Slab(ek, params, r, self.nranks, device, zchunk) for r in comm.local_ranks]
         self.t = 0.0
-        self.zchunks = 4              # pipeline depth of the Poisson transposes
         self.profile = False          # per-phase CUDA-event timing (development aid)
         self._ev = []
+        self.overlap = True           # forward half of the Poisson stage runs behind the LBM launches
+        self.K = 0
+        self.side = torch.cuda.Stream(device=self.slabs[0].dev)
+        self.set_poisson_chunks(4)
+
+    def set_poisson_chunks(self, nchunks: int):
+        """pipeline depth of the Poisson stage (groups of the LBM kernel's z-blocks)"""
+        ks = {s.setup_poisson(nchunks) for s in self.slabs}
+        assert len(ks) == 1
+        self.K = ks.pop()
 
     def _mark(self, name):
         if self.profile:
@@ -304,41 +332,63 @@ class SlabGroup:
         for s in self.slabs:
             s.ck(s.L.ek_phi_halo_unpack(s.h, C.c_void_p(s.p_from_l.data_ptr()), C.c_void_p(s.p_from_r.data_ptr())), "ek_phi_halo_unpack")
 
-    def poisson(self):
-        """the distributed fast_Poisson(): dq -> phi (interior, walls, ghost columns).
-        The planes are processed in `self.zchunks` chunks so that the all-to-all of
-        one chunk travels while the next chunk is being transformed."""
-        M = self.slabs[0].M
-        K = max(1, min(self.zchunks, M))
-        bounds = [(M * k // K, M * (k + 1) // K) for k in range(K)]
-        P = self.nranks
-        # y FFT + first transpose, chunk by chunk
+    def _a2a_start(self, k, which):
+        bufs = [(s.send[k], s.recv[k]) for s in self.slabs]
+        if bufs[0][0] is None:
+            return None
+        return self.comm.all_to_all_start([b[0] for b in bufs], [b[1] for b in bufs])
+
+    def _a2a_finish(self, hnd):
+        if hnd is not None:
+            self.comm.all_to_all_finish(hnd)
+
+    def poisson_forward(self, k: int):
+        """chunk k: re-blocking + y-transform of my columns, then its transpose starts"""
+        for s in self.slabs:
+            s.ck(s.L.ek_slab_poisson_forward(s.h, k), "ek_slab_poisson_forward")
+        return self._a2a_start(k, 0)
+
+    def poisson_rest(self, pending):
+        """everything after the forward halves were started: pencils, solve, way back"""
+        for k, hnd in enumerate(pending):
+            self._a2a_finish(hnd)
+            for s in self.slabs:
+                s.ck(s.L.ek_slab_poisson_gather_x(s.h, k), "ek_slab_poisson_gather_x")
+        self._mark("poisson_transpose_1_gather_x")
+        for s in self.slabs:
+            s.ck(s.L.ek_slab_poisson_solve(s.h), "ek_slab_poisson_solve")
+        self._mark("poisson_x_fft_zsolve_x_ifft")
         pending = []
-        for (a, b) in bounds:
-            send = [s.poisson_forward_local(a, b) for s in self.slabs]
-            pending.append(self.comm.all_to_all_start(send))
-        self._mark("poisson_y_fft_pack")
-        Xs = [torch.empty((M, s.kyl, s.NXg), dtype=torch.complex128, device=s.dev) for s in self.slabs]
-        for (a, b), hnd in zip(bounds, pending):
-            recv = self.comm.all_to_all_finish(hnd)
-            for s, X, r in zip(self.slabs, Xs, recv):
-                X[a:b] = x_forward(r)
-        self._mark("poisson_all_to_all_1_x_fft")
-        for s, X in zip(self.slabs, Xs):
-            s.zsolve(X)
-        self._mark("poisson_zsolve")
-        pending = []
-        for (a, b) in bounds:
-            send = [x_backward(X[a:b], P) for X in Xs]
-            pending.append(self.comm.all_to_all_start(send))
-        self._mark("poisson_x_ifft_pack")
-        for k, ((a, b), hnd) in enumerate(zip(bounds, pending)):
-            recv = self.comm.all_to_all_finish(hnd)
-            for s, r in zip(self.slabs, recv):
-                s.poisson_backward_local(r, a, b, last=(k == K - 1))
-        self._mark("poisson_all_to_all_2_y_ifft")
+        for k in range(self.K):
+            for s in self.slabs:
+                s.ck(s.L.ek_slab_poisson_scatter_x(s.h, k), "ek_slab_poisson_scatter_x")
+            pending.append(self._a2a_start(k, 1))
+        self._mark("poisson_scatter_x")
+        for k, hnd in enumerate(pending):
+            self._a2a_finish(hnd)
+            for s in self.slabs:
+                s.ck(s.L.ek_slab_poisson_backward(s.h, k), "ek_slab_poisson_backward")
+        for s in self.slabs:
+            s.ck(s.L.ek_poisson_finish(s.h, 0), "ek_poisson_finish")
+        self._mark("poisson_transpose_2_y_ifft")
         self.phi_halo_exchange()
         self._mark("phi_halo")
+
+    def poisson_reference(self):
+        """the same stage through torch.fft and un-chunked transposes (tests only)"""
+        recv = self.comm.all_to_all([s.poisson_forward_local() for s in self.slabs])
+        recv = self.comm.all_to_all([s.poisson_middle(r) for s, r in zip(self.slabs, recv)])
+        for s, r in zip(self.slabs, recv):
+            s.poisson_backward_local(r)
+        self.phi_halo_exchange()
+
+    def poisson(self):
+        """the distributed fast_Poisson(): dq -> phi (interior, walls, ghost columns).
+        The planes are processed in self.K chunks so that the all-to-all of one
+        chunk travels while the next chunk is being transformed."""
+        pending = [self.poisson_forward(k) for k in range(self.K)]
+        self._mark("poisson_y_fft")
+        self.poisson_rest(pending)
 
     # -- the reference's call sequence ---------------------------------------------
     def initialization(self):
@@ -374,19 +424,51 @@ class SlabGroup:
         self.initialization()
         self.init_equilibrium()
 
+    def lbm_and_forward(self, full: bool):
+        """One LBM pass launched chunk by chunk; chunk k's Poisson forward half
+        (re-blocking, y-transform, transpose 1) runs on a side stream as soon as
+        the launch that produces its planes has finished, behind the launches of
+        the later chunks."""
+        main = torch.cuda.current_stream()
+        pending = []
+        for k in range(self.K):
+            b0, b1 = self.slabs[0].blocks[k]
+            for s in self.slabs:
+                s.ck(s.L.ek_stream_collide_save_range(s.h, int(full), b0, b1, int(k == self.K - 1)),
+                     "ek_stream_collide_save_range")
+            ev = torch.cuda.Event()
+            ev.record(main)
+            self.side.wait_event(ev)
+            with torch.cuda.stream(self.side):
+                for s in self.slabs:
+                    s.ck(s.L.ek_switch_stream(s.h, C.c_void_p(self.side.cuda_stream)), "ek_switch_stream")
+                pending.append(self.poisson_forward(k))
+                for s in self.slabs:
+                    s.ck(s.L.ek_switch_stream(s.h, C.c_void_p(main.cuda_stream)), "ek_switch_stream")
+        main.wait_stream(self.side)
+        return pending
+
     def step(self, nsteps: int = 1):
         for i in range(nsteps):
             full = i == nsteps - 1
             parity = self.slabs[0].L.ek_lbm_parity(self.slabs[0].h)
             self._mark("begin")
-            for s in self.slabs:
-                s.sim.stream_collide_save(full)
-            self._mark("lbm")
+            if self.overlap and self.K > 1:
+                pending = self.lbm_and_forward(full)
+                self._mark("lbm_with_poisson_forward")
+            else:
+                for s in self.slabs:
+                    s.sim.stream_collide_save(full)
+                self._mark("lbm")
+                pending = None
             # the populations travel while the Poisson stage computes (independent data)
             phase = 0 if parity == 0 else 1
             hnd = self.halo_exchange_start(phase)
             self._mark("population_halo_pack")
-            self.poisson()
+            if pending is None:
+                self.poisson()
+            else:
+                self.poisson_rest(pending)
             self.halo_exchange_finish(phase, hnd)
             self._mark("population_halo_unpack")
             if full:
@@ -417,6 +499,9 @@ def bench_slabs(ek, dist, args, w, wl, local_rank):
     NX, NY, NZ = w["NX"], w["NY"], w["NZ"]
     p = ek.default_params(NX=NX, NY=NY, NZ=NZ, pb_iters=args.pb_iters, **w["over"])
     grp = SlabGroup(ek, p, comm, device=local_rank, zchunk=args.zchunk)
+    if getattr(args, "poisson_chunks", 4) != 4:
+        grp.set_poisson_chunks(args.poisson_chunks)
+    grp.overlap = not getattr(args, "no_overlap", False)
     t0 = time.time()
     grp.init()
     comm.barrier()
@@ -453,7 +538,8 @@ def bench_slabs(ek, dist, args, w, wl, local_rank):
             "higher_is_better": True, "scaling": "weak" if w.get("weak") else "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": w["name"], "grid": [NX, NY, NZ], "stream_mode": "aa", "zchunk": args.zchunk,
-                       "parallelism": f"x-slabs x{comm.nranks}: NCCL halo send/recv + all-to-all Poisson transposes",
+                       "parallelism": f"x-slabs x{comm.nranks}: NCCL halo send/recv + all-to-all Poisson transposes, "
+                                      f"{grp.K} z-chunks, forward half overlapped with the LBM launches",
                        "cells_per_gpu": cells // comm.nranks, "init": "reference start-up (PB iterations) %.2f s" % init_s,
                        "l2": "per-GPU working set >> 126 MB L2", "phase_ms_rank0": phases},
             "roofline": {"bound": "hbm", "achieved": round(step_gbs / comm.nranks, 1), "peak": peak, "unit": "GB/s",

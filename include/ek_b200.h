@@ -203,6 +203,27 @@ ek_status ek_dq_ptr(ek_handle *h, double **dev_ptr);
 ek_status ek_zsolve_columns(ek_handle *h, double *spec, int ky0, int kyl);
 ek_status ek_poisson_finish(ek_handle *h, int set_walls);
 ek_status ek_compute_efield(ek_handle *h);
+/* The distributed fast_Poisson() (replaces poisson.cu:75-103 on a domain split
+ * along x; ek_slab_poisson.cu): y-transform of my columns, slab transpose,
+ * x-transform + z-solve + inverse x-transform of my ky rows, transpose back,
+ * inverse y-transform into phi.  The planes are processed in `nchunks` groups
+ * of the LBM kernel's z-blocks so that the host can pipeline the transposes
+ * (and the LBM launches that produce the planes) against the transforms.
+ * Per chunk k the host runs
+ *     forward(k); all-to-all(send_k -> recv_k); gather_x(k)
+ * then solve() once, then per chunk
+ *     scatter_x(k); all-to-all(send_k -> recv_k); backward(k)
+ * and ek_poisson_finish().  send/recv hold `count` complex doubles in nranks
+ * equal parts (part i travels to / comes from rank i). */
+ek_status ek_slab_poisson_setup(ek_handle *h, int nchunks);
+int ek_slab_poisson_chunks(ek_handle *h);
+ek_status ek_slab_poisson_chunk(ek_handle *h, int k, int *block0, int *block1, void **send, void **recv,
+                                long long *count);
+ek_status ek_slab_poisson_forward(ek_handle *h, int k);
+ek_status ek_slab_poisson_gather_x(ek_handle *h, int k);
+ek_status ek_slab_poisson_solve(ek_handle *h);
+ek_status ek_slab_poisson_scatter_x(ek_handle *h, int k);
+ek_status ek_slab_poisson_backward(ek_handle *h, int k);
 /* the pieces of initialization() (LBM.cu:68-146) for a host-driven PB loop */
 ek_status ek_init_uniform(ek_handle *h);
 ek_status ek_pbe(ek_handle *h);
