@@ -147,7 +147,7 @@ __device__ __forceinline__ void scalar_node(const StepArgs &a, Sh &sh, const int
         if (LEAN) efield_lean(a, la, z, E); else efield_at<EARR>(a, nb, z, E);
         sh.E[0][lane] = E[0]; sh.E[1][lane] = E[1]; sh.E[2][lane] = E[2];
     }
-    if (FULL && act) a.fld[3 + s][nb.fc()] = m;  // charge, chargen, T (LBM.cu:811-813)
+    if (FULL && act) a.fld[3 + s][LEAN ? (size_t)z * c.plane + la.fc : (size_t)nb.fc()] = m;  // charge, chargen, T (LBM.cu:811-813)
     bar_moments<NT>();
     // E is read between the two barriers: the temperature warp may only
     // overwrite it after every warp has passed bar_velocity()
@@ -209,7 +209,7 @@ __device__ __forceinline__ void scalar_role(const StepArgs &a, Sh &sh, const int
     }
 
     for (int z = z0; z < z1; ++z) {
-        if (LEANOK && z >= 2 && z < c.NZ - 2) scalar_node<MODE, false, false, NT, true>(a, sh, s, lane, act, x, y, la, W, mom_sh, z);
+        if (LEANOK && z >= 2 && z < c.NZ - 2) scalar_node<MODE, FULL, false, NT, true>(a, sh, s, lane, act, x, y, la, W, mom_sh, z);
         else scalar_node<MODE, FULL, EARR, NT, false>(a, sh, s, lane, act, x, y, la, W, mom_sh, z);
     }
 }
@@ -317,7 +317,11 @@ __device__ __forceinline__ void fluid_node(const StepArgs &a, Sh &sh, const int 
     bar_velocity<NT>();
     if (act) {
         if (LEAN) {
-            a.dq[(size_t)z * c.plane + la.fc] = dq;
+            const size_t i = (size_t)z * c.plane + la.fc;
+            a.dq[i] = dq;
+            if (FULL) {  // LBM.cu:807-810
+                a.fld[0][i] = rho; a.fld[1][i] = u[0]; a.fld[2][i] = u[1]; a.fld[3][i] = u[2];
+            }
         } else {
             const int i = nb.fc();
             a.dq[i] = dq;
@@ -370,7 +374,7 @@ __device__ __forceinline__ void fluid_role(const StepArgs &a, Sh &sh, const int 
     }
 
     for (int z = z0; z < z1; ++z) {
-        if (LEANOK && z >= 2 && z < c.NZ - 2) fluid_node<MODE, false, NT, true>(a, sh, lane, act, x, y, la, expr1, z);
+        if (LEANOK && z >= 2 && z < c.NZ - 2) fluid_node<MODE, FULL, NT, true>(a, sh, lane, act, x, y, la, expr1, z);
         else fluid_node<MODE, FULL, NT, false>(a, sh, lane, act, x, y, la, expr1, z);
     }
 }
@@ -567,6 +571,7 @@ cudaError_t launch_mode(const StepArgs &a, bool full, bool earr, bool lean, dim3
     constexpr bool AA = (MODE != EK_MODE_PUSH);
     if (full) {
         if (earr) ek_step_kernel<MODE, true, true, false><<<grid, 128, 0, st>>>(a);
+        else if (lean && AA) ek_step_kernel<MODE, true, false, AA><<<grid, 128, 0, st>>>(a);
         else ek_step_kernel<MODE, true, false, false><<<grid, 128, 0, st>>>(a);
     } else {
         if (earr) ek_step_kernel<MODE, false, true, false><<<grid, 128, 0, st>>>(a);
