@@ -19,7 +19,7 @@ __global__ void k_dq_from_fields(EkConst c, const double *ch, const double *chn,
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= c.NX) return;
     const size_t i = (size_t)blockIdx.z * c.plane + blockIdx.y * c.PX + x;
-    dq[i] = ch[i] - chn[i];
+    dq[(size_t)blockIdx.z * c.dq_sz + (size_t)blockIdx.y * c.dq_sy + x] = ch[i] - chn[i];
 }
 
 }  // namespace
@@ -41,6 +41,8 @@ void ek_compute_consts(const ek_params &p, EkConst &c, bool slab)
     }
     c.plane = (long long)c.NY * c.PX;
     c.N = (long long)c.NZ * c.plane;
+    c.dq_sy = c.PX;
+    c.dq_sz = c.plane;
     c.NXT = (c.PX + EK_TILE - 1) / EK_TILE;
     c.lrow = (unsigned)c.NXT * EK_TILE_ELEMS;
     c.lplane = (unsigned)c.NY * c.lrow;

@@ -43,7 +43,7 @@ __global__ void k_pbe(EkConst c, double chargeinf, double electron, double kB, d
     const double b = chargeinf * exp(electron * fi[i] / kB / roomT);
     ch[i] = a;
     chn[i] = b;
-    dq[i] = a - b;
+    dq[(size_t)z * c.dq_sz + (size_t)y * c.dq_sy + x] = a - b;
 }
 
 // phi <- omega*phi + (1-omega)*phi_old ; phi_old <- phi  (LBM.cu:136, 101-104)

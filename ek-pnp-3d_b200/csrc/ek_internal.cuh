@@ -66,6 +66,8 @@ struct EkConst {
     int xlo, xhi;        // column index of the x-1 neighbour of x=0 and of the x+1 neighbour of x=NX-1
     long long plane;     // NY*PX
     long long N;         // NZ*NY*PX : elements per field array
+    long long dq_sy, dq_sz;  // c+ - c- lives at dq[z*dq_sz + y*dq_sy + x]: (PX, plane) like the fields, or
+                         // (NZ*NX, NX) = rows for the y-transform of the distributed Poisson stage
     int NXT;             // x-tiles per row of the population lattice: ceil(PX/32)
     unsigned lrow;       // lattice elements per (z,y) row:  NXT*27*32
     unsigned lplane;     // lattice elements per z plane:    NY*lrow
@@ -168,7 +170,8 @@ struct EkSlabPoisson {
     int K = 1;                        // z-chunks
     int z0[EK_MAX_CHUNKS + 1] = {};   // chunk bounds (interior-plane index 0..M)
     int block0[EK_MAX_CHUNKS + 1] = {};  // first LBM z-block of each chunk
-    double *A = nullptr;              // [NY][M][NXl] real: rows for the y-transforms
+    double *A = nullptr;              // [NY][NZ][NXl] real rows for the inverse y-transforms (the forward
+                                      // ones read c+ - c-, which the LBM kernel writes in this layout)
     cufftDoubleComplex *S = nullptr;  // send buffers, per chunk [P*kyl][nzc][NXl]
     cufftDoubleComplex *R = nullptr;  // receive buffers, same shape
     cufftDoubleComplex *X = nullptr;  // full-x pencils [kyl][M][NXg]

@@ -318,13 +318,13 @@ __device__ __forceinline__ void fluid_node(const StepArgs &a, Sh &sh, const int 
     if (act) {
         if (LEAN) {
             const size_t i = (size_t)z * c.plane + la.fc;
-            a.dq[i] = dq;
+            a.dq[(size_t)z * c.dq_sz + la.fdq] = dq;
             if (FULL) {  // LBM.cu:807-810
                 a.fld[0][i] = rho; a.fld[1][i] = u[0]; a.fld[2][i] = u[1]; a.fld[3][i] = u[2];
             }
         } else {
             const int i = nb.fc();
-            a.dq[i] = dq;
+            a.dq[dq_at(c, nb, z)] = dq;
             if (FULL) {  // LBM.cu:807-810
                 a.fld[0][i] = rho; a.fld[1][i] = u[0]; a.fld[2][i] = u[1]; a.fld[3][i] = u[2];
             }
@@ -356,6 +356,7 @@ __device__ __forceinline__ void fluid_role(const StepArgs &a, Sh &sh, const int 
         Nbr nb;
         set_xy(nb, c, x, y);
         lean_init(la, nb);
+        la.fdq = (long long)y * c.dq_sy + x;
     }
 
     if (z0 == 0) {
@@ -496,7 +497,7 @@ __device__ __forceinline__ void fluid_half_b(const StepArgs &a, Sh &sh, const in
         sh.rho[lane] = rho;
         sh.F[0][lane] = F[0]; sh.F[1][lane] = F[1]; sh.F[2][lane] = F[2];
         bar_velocity<NT>();
-        if (act) a.dq[nb.fc()] = dq;
+        if (act) a.dq[dq_at(c, nb, z)] = dq;
         const double wcr[4] = {c.w[0] * rho, c.w[1] * rho, c.w[2] * rho, c.w[3] * rho};
         const double omusq = 1.0 - 0.5 * (u[0] * u[0] + u[1] * u[1] + u[2] * u[2]) * c.inv_cs2;
         const double uF = u[0] * F[0] + u[1] * F[1] + u[2] * F[2];

@@ -218,7 +218,7 @@ __device__ __forceinline__ void warp_role(const StepArgs &a, Sh8 *sh, const int 
         if (fluid) {
             if (act) {
                 const int i = nb.fc();
-                if (HALF == 1) a.dq[i] = m.dq;
+                if (HALF == 1) a.dq[dq_at(c, nb, z)] = m.dq;
                 if (FULL && HALF == 0) {  // LBM.cu:807-810
                     a.fld[0][i] = m.rho; a.fld[1][i] = u[0]; a.fld[2][i] = u[1]; a.fld[3][i] = u[2];
                 }

@@ -15,6 +15,7 @@ namespace {
 struct Nbr {
     unsigned lx[3], ly[3], lz[3];  // lattice element offsets of x-1,x,x+1 / y-1,y,y+1 / z-1,z,z+1 (z periodic)
     int fx[3], fy[3], fz[3];       // the same for the field arrays
+    int yy;                        // row index (for the c+ - c- array, which has its own strides)
     __device__ __forceinline__ unsigned at(int ax, int ay, int az) const { return lz[az + 1] + ly[ay + 1] + lx[ax + 1]; }
     __device__ __forceinline__ unsigned lc() const { return lz[1] + ly[1] + lx[1]; }
     __device__ __forceinline__ int fc() const { return fz[1] + fy[1] + fx[1]; }
@@ -27,6 +28,7 @@ __device__ __forceinline__ void set_xy(Nbr &nb, const EkConst &c, int x, int y)
     nb.fx[2] = x == c.NX - 1 ? c.xhi : x + 1;
     const int ym = y == 0 ? c.NY - 1 : y - 1, yp = y == c.NY - 1 ? 0 : y + 1;
     nb.fy[0] = ym * c.PX; nb.fy[1] = y * c.PX; nb.fy[2] = yp * c.PX;
+    nb.yy = y;
 #pragma unroll
     for (int k = 0; k < 3; ++k) nb.lx[k] = ek_lat_col(nb.fx[k]);
     nb.ly[0] = (unsigned)ym * c.lrow; nb.ly[1] = (unsigned)y * c.lrow; nb.ly[2] = (unsigned)yp * c.lrow;
@@ -38,6 +40,12 @@ __device__ __forceinline__ void set_z(Nbr &nb, const EkConst &c, int z)
     const int zp = z == c.NZ - 1 ? 0 : z + 1;
     nb.fz[0] = (int)(zm * c.plane); nb.fz[1] = (int)(z * c.plane); nb.fz[2] = (int)(zp * c.plane);
     nb.lz[0] = (unsigned)zm * c.lplane; nb.lz[1] = (unsigned)z * c.lplane; nb.lz[2] = (unsigned)zp * c.lplane;
+}
+
+// index of a node in the c+ - c- array
+__device__ __forceinline__ size_t dq_at(const EkConst &c, const Nbr &nb, int z)
+{
+    return (size_t)z * c.dq_sz + (size_t)nb.yy * c.dq_sy + nb.fx[1];
 }
 
 // pre-collision populations of a node ("pull" restatement)
@@ -134,6 +142,7 @@ struct LeanAddr {
     unsigned oxy[3][3];  // [cy+1][cx+1]: lattice element offset of column (x+cx, y+cy) within a plane
     double *b[3];        // lattice base of the planes z-1, z, z+1
     int fc, fxm, fxp, fym, fyp;  // field offsets within a plane: centre, x-1, x+1, y-1, y+1
+    long long fdq;               // y*dq_sy + x of the c+ - c- array
 };
 
 // (forcing the address to ONE mad.wide.u32 with the offsets pinned in registers

@@ -5,9 +5,8 @@
 // x and y, second differences in z between the Dirichlet walls.  x is split over
 // the ranks, so the x-transform sits between two slab transposes:
 //
-//   c+ - c-  [z][y][x_local]
-//     k_planes_to_rows   -> A  [y][z][x_local]            (hand-written, one pass)
-//     cuFFT D2Z along y  -> S  [ky][z][x_local]           (strided batch, no packing pass:
+//   c+ - c-  [y][z][x_local]   (the LBM kernel writes it in this layout in slab mode: EkConst::dq_sy/dq_sz)
+//     cuFFT D2Z along y  -> S  [ky][z][x_local]           (ONE strided batch per chunk, no packing pass:
 //                                                          rows of S are already grouped by the
 //                                                          destination rank of the transpose)
 //     transpose 1: all-to-all over the ky blocks  (host: NCCL; or direct peer writes)
@@ -32,26 +31,15 @@
 
 namespace {
 
-// A[(y*M + zi)*NXl + x] = dq[(zi+1)*plane + y*PX + x]   for zi in [za, zb)
-__global__ void k_planes_to_rows(int NXl, int NY, int M, int PX, long long plane, int za,
-                                 const double *__restrict__ dq, double *__restrict__ A)
+// phi[z*plane + y*PX + x] = A[(y*NZ + z)*NXl + x]   for the planes z = za+1 .. of a chunk
+__global__ void k_rows_to_planes(int NXl, int NZ, int PX, long long plane, int za, const double *__restrict__ A,
+                                 double *__restrict__ phi)
 {
     const int x2 = blockIdx.x * blockDim.x + threadIdx.x;  // pairs of columns (NXl and PX are even)
     if (2 * x2 >= NXl) return;
-    const int y = blockIdx.y, zi = za + blockIdx.z;
-    const double2 v = *reinterpret_cast<const double2 *>(dq + (size_t)(zi + 1) * plane + (size_t)y * PX + 2 * x2);
-    *reinterpret_cast<double2 *>(A + ((size_t)y * M + zi) * NXl + 2 * x2) = v;
-}
-
-// phi[(zi+1)*plane + y*PX + x] = A[(y*M + zi)*NXl + x]   for zi in [za, zb)
-__global__ void k_rows_to_planes(int NXl, int NY, int M, int PX, long long plane, int za,
-                                 const double *__restrict__ A, double *__restrict__ phi)
-{
-    const int x2 = blockIdx.x * blockDim.x + threadIdx.x;
-    if (2 * x2 >= NXl) return;
-    const int y = blockIdx.y, zi = za + blockIdx.z;
-    const double2 v = *reinterpret_cast<const double2 *>(A + ((size_t)y * M + zi) * NXl + 2 * x2);
-    *reinterpret_cast<double2 *>(phi + (size_t)(zi + 1) * plane + (size_t)y * PX + 2 * x2) = v;
+    const int y = blockIdx.y, z = za + 1 + blockIdx.z;
+    const double2 v = *reinterpret_cast<const double2 *>(A + ((size_t)y * NZ + z) * NXl + 2 * x2);
+    *reinterpret_cast<double2 *>(phi + (size_t)z * plane + (size_t)y * PX + 2 * x2) = v;
 }
 
 // The two re-blockings around the transposes are copies of rows of NXl complex
@@ -80,11 +68,12 @@ ek_status plan_for(ek_handle *h, std::map<int, cufftHandle> &plans, int nzc, boo
     cufftHandle plan;
     int n[1] = {S.NY};
     int emb[1] = {S.NY};
+    const int NZ = S.M + 2;
     if (forward) {
-        // in: A + za*NXl, element (y; b) at y*(M*NXl) + b;  out: chunk buffer, (ky; b) at ky*(nzc*NXl) + b
-        EK_CUFFT(h, cufftPlanMany(&plan, 1, n, emb, S.M * S.NXl, 1, emb, nzc * S.NXl, 1, CUFFT_D2Z, nzc * S.NXl));
+        // in: dq + (za+1)*NXl, element (y; b) at y*(NZ*NXl) + b;  out: chunk buffer, (ky; b) at ky*(nzc*NXl) + b
+        EK_CUFFT(h, cufftPlanMany(&plan, 1, n, emb, NZ * S.NXl, 1, emb, nzc * S.NXl, 1, CUFFT_D2Z, nzc * S.NXl));
     } else {
-        EK_CUFFT(h, cufftPlanMany(&plan, 1, n, emb, nzc * S.NXl, 1, emb, S.M * S.NXl, 1, CUFFT_Z2D, nzc * S.NXl));
+        EK_CUFFT(h, cufftPlanMany(&plan, 1, n, emb, nzc * S.NXl, 1, emb, NZ * S.NXl, 1, CUFFT_Z2D, nzc * S.NXl));
     }
     plans[nzc] = plan;
     return EK_OK;
@@ -138,7 +127,7 @@ ek_status ek_slab_poisson_setup(ek_handle *h, int nchunks)
         if (k == S.K) zi = S.M;
         S.z0[k] = zi;
     }
-    const size_t nreal = (size_t)S.NY * S.M * S.NXl;
+    const size_t nreal = (size_t)S.NY * c.NZ * S.NXl;
     const size_t nspec = (size_t)S.P * S.kyl * S.M * S.NXl;
     const size_t npen = (size_t)S.kyl * S.M * S.NXg;
     EK_CUDA(h, cudaMalloc((void **)&S.A, nreal * sizeof(double)));
@@ -170,6 +159,10 @@ ek_status ek_slab_poisson_setup(ek_handle *h, int nchunks)
     for (int i = 0; i < EK_MAX_RANKS; ++i) { S.peerX[i] = nullptr; S.peerR[i] = nullptr; }
     S.peerX[S.r] = S.X;
     S.peerR[S.r] = S.R;
+    // from now on c+ - c- is kept as rows for the y-transform: [y][z][x] without ghost columns
+    // (the allocation of NZ*NY*PX doubles is large enough); whoever wrote it before must write it again
+    h->c.dq_sy = (long long)c.NZ * S.NXl;
+    h->c.dq_sz = S.NXl;
     S.ready = true;
     return EK_OK;
 }
@@ -201,9 +194,6 @@ ek_status ek_slab_poisson_forward(ek_handle *h, int k)
     const EkConst &c = h->c;
     const int za = S.z0[k], nzc = S.z0[k + 1] - za;
     if (nzc <= 0) return EK_OK;
-    dim3 b(128), gr((S.NXl / 2 + 127) / 128, S.NY, nzc);
-    k_planes_to_rows<<<gr, b, 0, h->stream>>>(S.NXl, S.NY, S.M, c.PX, c.plane, za, h->dq, S.A);
-    EK_CUDA(h, cudaGetLastError());
     cufftHandle plan = S.plan_yf[nzc];
     cufftDoubleComplex *out = S.S + (size_t)S.P * S.kyl * za * S.NXl;
     // rows ky >= NY/2+1 (padding of the last rank's block) are not written by the transform
@@ -211,7 +201,7 @@ ek_status ek_slab_poisson_forward(ek_handle *h, int k)
         EK_CUDA(h, cudaMemsetAsync(out + (size_t)S.NYH * nzc * S.NXl, 0,
                                    (size_t)(S.P * S.kyl - S.NYH) * nzc * S.NXl * sizeof(cufftDoubleComplex), h->stream));
     EK_CUFFT(h, cufftSetStream(plan, h->stream));
-    EK_CUFFT(h, cufftExecD2Z(plan, S.A + (size_t)za * S.NXl, out));
+    EK_CUFFT(h, cufftExecD2Z(plan, h->dq + (size_t)(za + 1) * S.NXl, out));
     h->poisson_launches += 1;
     return EK_OK;
 }
@@ -291,9 +281,9 @@ ek_status ek_slab_poisson_backward(ek_handle *h, int k)
     if (nzc <= 0) return EK_OK;
     cufftHandle plan = S.plan_yb[nzc];
     EK_CUFFT(h, cufftSetStream(plan, h->stream));
-    EK_CUFFT(h, cufftExecZ2D(plan, S.R + (size_t)S.P * S.kyl * za * S.NXl, S.A + (size_t)za * S.NXl));
+    EK_CUFFT(h, cufftExecZ2D(plan, S.R + (size_t)S.P * S.kyl * za * S.NXl, S.A + (size_t)(za + 1) * S.NXl));
     dim3 b(128), gr((S.NXl / 2 + 127) / 128, S.NY, nzc);
-    k_rows_to_planes<<<gr, b, 0, h->stream>>>(S.NXl, S.NY, S.M, c.PX, c.plane, za, S.A, h->fld[EK_PHI]);
+    k_rows_to_planes<<<gr, b, 0, h->stream>>>(S.NXl, c.NZ, c.PX, c.plane, za, S.A, h->fld[EK_PHI]);
     EK_CUDA(h, cudaGetLastError());
     h->poisson_launches += 1;
     return EK_OK;

@@ -218,7 +218,8 @@ class Slab:
         self.PX = self.L.ek_row_pitch(self.h)
         p = C.c_void_p()
         self.sim._ck(self.L.ek_dq_ptr(self.h, C.byref(p)), "ek_dq_ptr")
-        self.dq = device_view(p.value, (self.NZ, self.NY, self.PX), self.dev)
+        self._dq_flat = device_view(p.value, (self.NZ * self.NY * self.PX,), self.dev)
+        self.dq = self._dq_flat.view(self.NZ, self.NY, self.PX)
         self.sim._ck(self.L.ek_field_ptr(self.h, ek.FIELDS.index("phi"), C.byref(p)), "ek_field_ptr")
         self.phi = device_view(p.value, (self.NZ, self.NY, self.PX), self.dev)
         nh = self.L.ek_halo_doubles(self.h)
@@ -233,6 +234,8 @@ class Slab:
         """native distributed Poisson stage: chunk buffers as torch views for the transport"""
         self.ck(self.L.ek_slab_poisson_setup(self.h, int(nchunks)), "ek_slab_poisson_setup")
         K = self.L.ek_slab_poisson_chunks(self.h)
+        # c+ - c- is now kept as [y][z][x] rows without ghost columns (EkConst::dq_sy/dq_sz)
+        self.dq = self._dq_flat.as_strided((self.NZ, self.NY, self.NX), (self.NX, self.NZ * self.NX, 1))
         self.send, self.recv, self.blocks = [], [], []
         for k in range(K):
             b0, b1, cnt = C.c_int(), C.c_int(), C.c_longlong()
