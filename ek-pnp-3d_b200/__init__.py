@@ -114,8 +114,13 @@ def load_library():
     L.ek_slab_poisson_chunks.argtypes = [H]
     L.ek_slab_poisson_chunk.argtypes = [H, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_void_p),
                                         C.POINTER(C.c_void_p), C.POINTER(C.c_longlong)]
+    L.ek_slab_poisson_ipc_bytes.argtypes = []
+    L.ek_slab_poisson_ipc_export.argtypes = [H, C.c_void_p]
+    L.ek_slab_poisson_ipc_import.argtypes = [H, C.c_int, C.c_void_p]
+    L.ek_slab_poisson_set_peer.argtypes = [H, C.c_int, C.c_void_p, C.c_void_p]
+    L.ek_slab_poisson_my_buffers.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     for name in ("ek_slab_poisson_forward", "ek_slab_poisson_gather_x", "ek_slab_poisson_scatter_x",
-                 "ek_slab_poisson_backward"):
+                 "ek_slab_poisson_backward", "ek_slab_poisson_push_x", "ek_slab_poisson_push_back"):
         getattr(L, name).argtypes = [H, C.c_int]
     L.ek_slab_poisson_solve.argtypes = [H]
     L.ek_adopt_field.argtypes = [H, C.c_int, C.c_void_p]

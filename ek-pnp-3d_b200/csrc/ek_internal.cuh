@@ -181,6 +181,7 @@ struct EkSlabPoisson {
     bool plan_x_ok = false;
     cufftDoubleComplex *peerX[EK_MAX_RANKS] = {};  // direct peer-memory transport (optional)
     cufftDoubleComplex *peerR[EK_MAX_RANKS] = {};
+    bool peer_ipc[EK_MAX_RANKS] = {};              // mapped through CUDA IPC (to be closed)
 };
 void ek_slab_poisson_destroy(ek_handle *h);
 

@@ -90,6 +90,11 @@ void ek_slab_poisson_destroy(ek_handle *h)
     S.plan_yb.clear();
     if (S.plan_x_ok) cufftDestroy(S.plan_x);
     S.plan_x_ok = false;
+    for (int i = 0; i < EK_MAX_RANKS; ++i) {
+        if (S.peer_ipc[i]) { cudaIpcCloseMemHandle(S.peerX[i]); cudaIpcCloseMemHandle(S.peerR[i]); }
+        S.peer_ipc[i] = false;
+        S.peerX[i] = S.peerR[i] = nullptr;
+    }
     cudaFree(S.A); cudaFree(S.S); cudaFree(S.R); cudaFree(S.X); cudaFree(S.cp);
     S.A = nullptr; S.S = S.R = S.X = nullptr; S.cp = nullptr;
     S.ready = false;
@@ -262,6 +267,113 @@ ek_status ek_slab_poisson_scatter_x(ek_handle *h, int k)
     for (int i = 0; i < S.P; ++i) {
         p.src[i] = X + (size_t)za * S.NXg + (size_t)i * S.NXl;
         p.dst[i] = Sd + (size_t)i * S.kyl * nzc * S.NXl;
+    }
+    dim3 b(128), gr((S.NXl + 127) / 128, S.kyl * nzc, S.P);
+    k_copy_rows<<<gr, b, 0, h->stream>>>(p, S.NXl, nzc, (long long)S.M * S.NXg, S.NXg, (long long)nzc * S.NXl, S.NXl);
+    EK_CUDA(h, cudaGetLastError());
+    h->poisson_launches += 1;
+    return EK_OK;
+}
+
+// ---- direct peer-memory transport of the two transposes ------------------------------
+// Every rank maps the pencil buffer X and the receive buffer R of every other rank (CUDA
+// IPC between the processes of one node; plain pointers when the slabs share a process).
+// The re-blocking kernel then writes its rows straight into the peers' buffers over
+// NVLink: push_x(k) = all-to-all 1 + gather_x(k), push_back(k) = scatter_x(k) + all-to-all 2,
+// without the intermediate send/receive copies.  The host provides the cross-rank
+// barriers: one after the push_x of all chunks, one after the push_back of all chunks.
+ek_status ek_slab_poisson_ipc_export(ek_handle *h, void *handles)
+{
+    if (!h || !h->sp.ready || !handles) return EK_ERR_INVALID;
+    DeviceGuard g(h->device);
+    cudaIpcMemHandle_t hx, hr;
+    EK_CUDA(h, cudaIpcGetMemHandle(&hx, h->sp.X));
+    EK_CUDA(h, cudaIpcGetMemHandle(&hr, h->sp.R));
+    memcpy(handles, &hx, sizeof(hx));
+    memcpy((char *)handles + sizeof(hx), &hr, sizeof(hr));
+    return EK_OK;
+}
+
+int ek_slab_poisson_ipc_bytes(void) { return (int)(2 * sizeof(cudaIpcMemHandle_t)); }
+
+ek_status ek_slab_poisson_ipc_import(ek_handle *h, int rank, const void *handles)
+{
+    if (!h || !h->sp.ready || !handles || rank < 0 || rank >= h->sp.P) return EK_ERR_INVALID;
+    if (rank == h->sp.r) return EK_OK;
+    DeviceGuard g(h->device);
+    cudaIpcMemHandle_t hx, hr;
+    memcpy(&hx, handles, sizeof(hx));
+    memcpy(&hr, (const char *)handles + sizeof(hx), sizeof(hr));
+    void *px = nullptr, *pr = nullptr;
+    EK_CUDA(h, cudaIpcOpenMemHandle(&px, hx, cudaIpcMemLazyEnablePeerAccess));
+    EK_CUDA(h, cudaIpcOpenMemHandle(&pr, hr, cudaIpcMemLazyEnablePeerAccess));
+    h->sp.peerX[rank] = (cufftDoubleComplex *)px;
+    h->sp.peerR[rank] = (cufftDoubleComplex *)pr;
+    h->sp.peer_ipc[rank] = true;
+    return EK_OK;
+}
+
+// peers living in this process (single-GPU tests): their buffers as plain pointers
+ek_status ek_slab_poisson_set_peer(ek_handle *h, int rank, void *X, void *R)
+{
+    if (!h || !h->sp.ready || rank < 0 || rank >= h->sp.P) return EK_ERR_INVALID;
+    h->sp.peerX[rank] = (cufftDoubleComplex *)X;
+    h->sp.peerR[rank] = (cufftDoubleComplex *)R;
+    return EK_OK;
+}
+
+ek_status ek_slab_poisson_my_buffers(ek_handle *h, void **X, void **R)
+{
+    if (!h || !h->sp.ready || !X || !R) return EK_ERR_INVALID;
+    *X = h->sp.X;
+    *R = h->sp.R;
+    return EK_OK;
+}
+
+static bool peers_ready(const EkSlabPoisson &S)
+{
+    for (int i = 0; i < S.P; ++i)
+        if (!S.peerX[i] || !S.peerR[i]) return false;
+    return true;
+}
+
+// y-spectrum of chunk k (my send buffer) -> every rank's pencils
+ek_status ek_slab_poisson_push_x(ek_handle *h, int k)
+{
+    if (!h || !h->sp.ready || k < 0 || k >= h->sp.K) return EK_ERR_INVALID;
+    EkSlabPoisson &S = h->sp;
+    if (!peers_ready(S)) { ek_set_error(h, "peer buffers not mapped"); return EK_ERR_STATE; }
+    DeviceGuard g(h->device);
+    const int za = S.z0[k], nzc = S.z0[k + 1] - za;
+    if (nzc <= 0) return EK_OK;
+    RowPtrs p;
+    const double2 *Ss = reinterpret_cast<const double2 *>(S.S) + (size_t)S.P * S.kyl * za * S.NXl;
+    for (int i = 0; i < S.P; ++i) {
+        p.src[i] = Ss + (size_t)i * S.kyl * nzc * S.NXl;                                      // rank i's ky rows
+        p.dst[i] = reinterpret_cast<double2 *>(S.peerX[i]) + (size_t)za * S.NXg + (size_t)S.r * S.NXl;  // my columns there
+    }
+    dim3 b(128), gr((S.NXl + 127) / 128, S.kyl * nzc, S.P);
+    k_copy_rows<<<gr, b, 0, h->stream>>>(p, S.NXl, nzc, (long long)nzc * S.NXl, S.NXl, (long long)S.M * S.NXg, S.NXg);
+    EK_CUDA(h, cudaGetLastError());
+    h->poisson_launches += 1;
+    return EK_OK;
+}
+
+// my pencils of chunk k -> every rank's receive buffer (its x block of my ky rows)
+ek_status ek_slab_poisson_push_back(ek_handle *h, int k)
+{
+    if (!h || !h->sp.ready || k < 0 || k >= h->sp.K) return EK_ERR_INVALID;
+    EkSlabPoisson &S = h->sp;
+    if (!peers_ready(S)) { ek_set_error(h, "peer buffers not mapped"); return EK_ERR_STATE; }
+    DeviceGuard g(h->device);
+    const int za = S.z0[k], nzc = S.z0[k + 1] - za;
+    if (nzc <= 0) return EK_OK;
+    RowPtrs p;
+    const double2 *X = reinterpret_cast<const double2 *>(S.X);
+    for (int i = 0; i < S.P; ++i) {
+        p.src[i] = X + (size_t)za * S.NXg + (size_t)i * S.NXl;
+        p.dst[i] = reinterpret_cast<double2 *>(S.peerR[i]) + (size_t)S.P * S.kyl * za * S.NXl
+                   + (size_t)S.r * S.kyl * nzc * S.NXl;
     }
     dim3 b(128), gr((S.NXl + 127) / 128, S.kyl * nzc, S.P);
     k_copy_rows<<<gr, b, 0, h->stream>>>(p, S.NXl, nzc, (long long)S.M * S.NXg, S.NXg, (long long)nzc * S.NXl, S.NXl);

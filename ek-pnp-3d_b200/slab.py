@@ -130,6 +130,21 @@ class LocalComm:
     def barrier(self):
         torch.cuda.synchronize()
 
+    def stream_barrier(self):
+        """cross-rank barrier in stream order: the slabs of this process share the stream"""
+
+    def map_peers(self, slabs) -> bool:
+        """direct peer-memory transport: every slab gets the others' buffers as plain pointers"""
+        ptrs = {}
+        for s in slabs:
+            X, R = C.c_void_p(), C.c_void_p()
+            s.ck(s.L.ek_slab_poisson_my_buffers(s.h, C.byref(X), C.byref(R)), "ek_slab_poisson_my_buffers")
+            ptrs[s.rank] = (X.value, R.value)
+        for s in slabs:
+            for r, (X, R) in ptrs.items():
+                s.ck(s.L.ek_slab_poisson_set_peer(s.h, r, C.c_void_p(X), C.c_void_p(R)), "ek_slab_poisson_set_peer")
+        return True
+
     def max_over_ranks(self, x: float) -> float:
         return x
 
@@ -180,6 +195,37 @@ class DistComm:
         self.dist.barrier()
         if torch.cuda.is_available():
             torch.cuda.synchronize()
+
+    def stream_barrier(self):
+        """cross-rank barrier in stream order (no host synchronisation): a one-element
+        all-reduce starts after this rank's preceding kernels and completes only once
+        every rank has joined; the kernels issued after it wait for it"""
+        if self.nranks > 1:
+            if not hasattr(self, "_flag"):
+                self._flag = torch.zeros(1, dtype=torch.float32, device="cuda")
+            self.dist.all_reduce(self._flag)
+
+    def map_peers(self, slabs) -> bool:
+        """direct peer-memory transport: exchange CUDA IPC handles of the pencil and
+        receive buffers; False (on every rank) if any mapping failed"""
+        s = slabs[0]
+        n = s.L.ek_slab_poisson_ipc_bytes()
+        mine = (C.c_ubyte * n)()
+        ok = s.L.ek_slab_poisson_ipc_export(s.h, mine) == 0
+        t = torch.tensor(list(mine), dtype=torch.uint8, device="cuda")
+        every = [torch.empty_like(t) for _ in range(self.nranks)]
+        self.dist.all_gather(every, t)
+        if ok:
+            for r, tr in enumerate(every):
+                if r == self.rank:
+                    continue
+                buf = (C.c_ubyte * n)(*tr.cpu().tolist())
+                if s.L.ek_slab_poisson_ipc_import(s.h, r, buf) != 0:
+                    ok = False
+                    break
+        flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
+        self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN)
+        return bool(flag.item() > 0.5)
 
     def max_over_ranks(self, x: float) -> float:
         t = torch.tensor([x], dtype=torch.float64, device="cuda" if torch.cuda.is_available() else "cpu")
@@ -284,6 +330,7 @@ class SlabGroup:
         self.overlap = True           # forward half of the Poisson stage runs behind the LBM launches
         self.K = 0
         self.side = torch.cuda.Stream(device=self.slabs[0].dev)
+        self.transport = "nccl"       # "nccl": all-to-all of the chunk buffers; "p2p": direct peer-memory writes
         self.set_poisson_chunks(4)
 
     def set_poisson_chunks(self, nchunks: int):
@@ -291,6 +338,18 @@ class SlabGroup:
         ks = {s.setup_poisson(nchunks) for s in self.slabs}
         assert len(ks) == 1
         self.K = ks.pop()
+        if self.transport == "p2p":
+            self.set_transport("p2p")     # the buffers were re-allocated: map them again
+
+    def set_transport(self, transport: str) -> str:
+        """"p2p": the re-blocking kernels write straight into the peers' buffers over NVLink
+        (CUDA IPC); falls back to "nccl" when the buffers cannot be mapped"""
+        if transport == "p2p":
+            self.comm.barrier()
+            transport = "p2p" if self.comm.map_peers(self.slabs) else "nccl"
+            self.comm.barrier()
+        self.transport = transport
+        return transport
 
     def _mark(self, name):
         if self.profile:
@@ -349,10 +408,16 @@ class SlabGroup:
         """chunk k: re-blocking + y-transform of my columns, then its transpose starts"""
         for s in self.slabs:
             s.ck(s.L.ek_slab_poisson_forward(s.h, k), "ek_slab_poisson_forward")
+        if self.transport == "p2p":
+            for s in self.slabs:
+                s.ck(s.L.ek_slab_poisson_push_x(s.h, k), "ek_slab_poisson_push_x")
+            return None
         return self._a2a_start(k, 0)
 
     def poisson_rest(self, pending):
         """everything after the forward halves were started: pencils, solve, way back"""
+        if self.transport == "p2p":
+            return self._poisson_rest_p2p()
         for k, hnd in enumerate(pending):
             self._a2a_finish(hnd)
             for s in self.slabs:
@@ -384,6 +449,26 @@ class SlabGroup:
         for s, r in zip(self.slabs, recv):
             s.poisson_backward_local(r)
         self.phi_halo_exchange()
+
+    def _poisson_rest_p2p(self):
+        self.comm.stream_barrier()            # every rank's rows have landed in my pencils
+        self._mark("poisson_transpose_1_barrier")
+        for s in self.slabs:
+            s.ck(s.L.ek_slab_poisson_solve(s.h), "ek_slab_poisson_solve")
+        self._mark("poisson_x_fft_zsolve_x_ifft")
+        for k in range(self.K):
+            for s in self.slabs:
+                s.ck(s.L.ek_slab_poisson_push_back(s.h, k), "ek_slab_poisson_push_back")
+        self.comm.stream_barrier()            # every rank's x blocks have landed in my receive buffer
+        self._mark("poisson_transpose_2_push")
+        for k in range(self.K):
+            for s in self.slabs:
+                s.ck(s.L.ek_slab_poisson_backward(s.h, k), "ek_slab_poisson_backward")
+        for s in self.slabs:
+            s.ck(s.L.ek_poisson_finish(s.h, 0), "ek_poisson_finish")
+        self._mark("poisson_y_ifft")
+        self.phi_halo_exchange()
+        self._mark("phi_halo")
 
     def poisson(self):
         """the distributed fast_Poisson(): dq -> phi (interior, walls, ghost columns).
@@ -505,6 +590,7 @@ def bench_slabs(ek, dist, args, w, wl, local_rank):
     if getattr(args, "poisson_chunks", 4) != 4:
         grp.set_poisson_chunks(args.poisson_chunks)
     grp.overlap = not getattr(args, "no_overlap", False)
+    transport = grp.set_transport(getattr(args, "transport", "nccl"))
     t0 = time.time()
     grp.init()
     comm.barrier()
@@ -541,7 +627,8 @@ def bench_slabs(ek, dist, args, w, wl, local_rank):
             "higher_is_better": True, "scaling": "weak" if w.get("weak") else "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": w["name"], "grid": [NX, NY, NZ], "stream_mode": "aa", "zchunk": args.zchunk,
-                       "parallelism": f"x-slabs x{comm.nranks}: NCCL halo send/recv + all-to-all Poisson transposes, "
+                       "parallelism": f"x-slabs x{comm.nranks}: NCCL halo send/recv + Poisson transposes by "
+                                      + ("NCCL all-to-all, " if transport == "nccl" else "direct peer-memory writes (CUDA IPC), ") +
                                       f"{grp.K} z-chunks, forward half overlapped with the LBM launches",
                        "cells_per_gpu": cells // comm.nranks, "init": "reference start-up (PB iterations) %.2f s" % init_s,
                        "l2": "per-GPU working set >> 126 MB L2", "phase_ms_rank0": phases},

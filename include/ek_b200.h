@@ -224,6 +224,22 @@ ek_status ek_slab_poisson_gather_x(ek_handle *h, int k);
 ek_status ek_slab_poisson_solve(ek_handle *h);
 ek_status ek_slab_poisson_scatter_x(ek_handle *h, int k);
 ek_status ek_slab_poisson_backward(ek_handle *h, int k);
+/* Direct peer-memory transport of the two transposes (one node, NVLink): every
+ * rank maps the pencil and receive buffers of every other rank -- CUDA IPC
+ * handles exported here and exchanged by the host (ipc_bytes() bytes per rank),
+ * or plain pointers for slabs of the same process -- and the re-blocking kernel
+ * writes its rows straight into them:
+ *     push_x(k)    = all-to-all 1 + gather_x(k)
+ *     push_back(k) = scatter_x(k) + all-to-all 2
+ * The host provides a cross-rank barrier after the push_x of all chunks and
+ * another after the push_back of all chunks. */
+int ek_slab_poisson_ipc_bytes(void);
+ek_status ek_slab_poisson_ipc_export(ek_handle *h, void *handles);
+ek_status ek_slab_poisson_ipc_import(ek_handle *h, int rank, const void *handles);
+ek_status ek_slab_poisson_set_peer(ek_handle *h, int rank, void *X, void *R);
+ek_status ek_slab_poisson_my_buffers(ek_handle *h, void **X, void **R);
+ek_status ek_slab_poisson_push_x(ek_handle *h, int k);
+ek_status ek_slab_poisson_push_back(ek_handle *h, int k);
 /* the pieces of initialization() (LBM.cu:68-146) for a host-driven PB loop */
 ek_status ek_init_uniform(ek_handle *h);
 ek_status ek_pbe(ek_handle *h);

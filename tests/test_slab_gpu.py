@@ -123,3 +123,22 @@ def test_overlapped_and_plain_slab_steps_are_bitwise_identical(ek, slab):
         grp.close()
     for k in util.FIELDS:
         assert np.array_equal(res[0][k], res[1][k]), k
+
+
+def test_peer_memory_transport_is_bitwise_identical_to_the_all_to_all(ek, slab):
+    """push_x / push_back (re-blocking kernels writing straight into the peers' buffers)
+    against all-to-all + local re-blocking: same numbers, same order, so bit for bit"""
+    over = dict(NX=96, NY=6, NZ=13, exf=1.0e6, voltage2=-3.0e-3)
+    init = synthetic_init(over)
+    res = []
+    for transport in ("nccl", "p2p"):
+        grp = slab.SlabGroup(ek, ek.default_params(**over), slab.LocalComm(3), zchunk=4)
+        assert grp.set_transport(transport) == transport
+        grp.set_fields(init)
+        grp.init_equilibrium()
+        grp.step(2)
+        grp.step(3)
+        res.append(grp.gather_fields())
+        grp.close()
+    for k in util.FIELDS:
+        assert np.array_equal(res[0][k], res[1][k]), k
