@@ -330,6 +330,7 @@ class SlabGroup:
         self.overlap = True           # forward half of the Poisson stage runs behind the LBM launches
         self.K = 0
         self.side = torch.cuda.Stream(device=self.slabs[0].dev)
+        self.halo_stream = torch.cuda.Stream(device=self.slabs[0].dev)
         self.transport = "nccl"       # "nccl": all-to-all of the chunk buffers; "p2p": direct peer-memory writes
         self.set_poisson_chunks(4)
 
@@ -512,6 +513,24 @@ class SlabGroup:
         self.initialization()
         self.init_equilibrium()
 
+    def _on_stream(self, stream):
+        """context: torch's current stream and the handles' stream are `stream`"""
+        grp = self
+
+        class _Ctx:
+            def __enter__(self):
+                self.main = torch.cuda.current_stream()
+                self.ctx = torch.cuda.stream(stream)
+                self.ctx.__enter__()
+                for s in grp.slabs:
+                    s.ck(s.L.ek_switch_stream(s.h, C.c_void_p(stream.cuda_stream)), "ek_switch_stream")
+
+            def __exit__(self, *exc):
+                for s in grp.slabs:
+                    s.ck(s.L.ek_switch_stream(s.h, C.c_void_p(self.main.cuda_stream)), "ek_switch_stream")
+                self.ctx.__exit__(*exc)
+        return _Ctx()
+
     def lbm_and_forward(self, full: bool):
         """One LBM pass launched chunk by chunk; chunk k's Poisson forward half
         (re-blocking, y-transform, transpose 1) runs on a side stream as soon as
@@ -527,12 +546,8 @@ class SlabGroup:
             ev = torch.cuda.Event()
             ev.record(main)
             self.side.wait_event(ev)
-            with torch.cuda.stream(self.side):
-                for s in self.slabs:
-                    s.ck(s.L.ek_switch_stream(s.h, C.c_void_p(self.side.cuda_stream)), "ek_switch_stream")
+            with self._on_stream(self.side):
                 pending.append(self.poisson_forward(k))
-                for s in self.slabs:
-                    s.ck(s.L.ek_switch_stream(s.h, C.c_void_p(main.cuda_stream)), "ek_switch_stream")
         main.wait_stream(self.side)
         return pending
 
@@ -549,16 +564,21 @@ class SlabGroup:
                     s.sim.stream_collide_save(full)
                 self._mark("lbm")
                 pending = None
-            # the populations travel while the Poisson stage computes (independent data)
+            # the populations travel while the Poisson stage computes (independent data):
+            # pack, NCCL send/recv and unpack run on their own stream next to the Poisson kernels
             phase = 0 if parity == 0 else 1
-            hnd = self.halo_exchange_start(phase)
-            self._mark("population_halo_pack")
+            main = torch.cuda.current_stream()
+            self.halo_stream.wait_stream(main)
+            with self._on_stream(self.halo_stream):
+                hnd = self.halo_exchange_start(phase)
             if pending is None:
                 self.poisson()
             else:
                 self.poisson_rest(pending)
-            self.halo_exchange_finish(phase, hnd)
-            self._mark("population_halo_unpack")
+            with self._on_stream(self.halo_stream):
+                self.halo_exchange_finish(phase, hnd)
+            main.wait_stream(self.halo_stream)
+            self._mark("population_halo_tail")
             if full:
                 for s in self.slabs:
                     s.ck(s.L.ek_compute_efield(s.h), "ek_compute_efield")
