@@ -218,7 +218,7 @@ def main():
     ap.add_argument("--kernel", type=int, default=None, help="LBM kernel variant (ek_set_option kernel)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--poisson-chunks", type=int, default=4, help="N>1: z-chunks of the distributed Poisson stage")
-    ap.add_argument("--transport", default="nccl", choices=["nccl", "p2p"],
+    ap.add_argument("--transport", default="nccl", choices=["nccl", "p2p", "dma"],
                     help="N>1: Poisson transposes by NCCL all-to-all or by direct peer-memory writes (CUDA IPC)")
     ap.add_argument("--no-overlap", action="store_true",
                     help="N>1: do not run the Poisson forward half behind the LBM launches")

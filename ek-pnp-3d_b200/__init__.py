@@ -115,6 +115,7 @@ def load_library():
     L.ek_slab_poisson_chunk.argtypes = [H, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_void_p),
                                         C.POINTER(C.c_void_p), C.POINTER(C.c_longlong)]
     L.ek_slab_poisson_ipc_bytes.argtypes = []
+    L.ek_slab_poisson_set_dma.argtypes = [H, C.c_int]
     L.ek_slab_poisson_ipc_export.argtypes = [H, C.c_void_p]
     L.ek_slab_poisson_ipc_import.argtypes = [H, C.c_int, C.c_void_p]
     L.ek_slab_poisson_set_peer.argtypes = [H, C.c_int, C.c_void_p, C.c_void_p]

@@ -182,6 +182,7 @@ struct EkSlabPoisson {
     cufftDoubleComplex *peerX[EK_MAX_RANKS] = {};  // direct peer-memory transport (optional)
     cufftDoubleComplex *peerR[EK_MAX_RANKS] = {};
     bool peer_ipc[EK_MAX_RANKS] = {};              // mapped through CUDA IPC (to be closed)
+    bool dma = false;                              // pushes by strided copies on the copy engines
 };
 void ek_slab_poisson_destroy(ek_handle *h);
 

@@ -330,6 +330,21 @@ ek_status ek_slab_poisson_my_buffers(ek_handle *h, void **X, void **R)
     return EK_OK;
 }
 
+// rows (ky, zi) of NXl complex numbers, [kyl][nzc] of them, between two pitched layouts: one strided
+// 3-D copy on the copy engines (NVLink DMA for a peer destination) instead of SM loads/stores
+static cudaError_t copy_rows_dma(const void *src, size_t src_row_bytes, size_t src_rows_per_ky, void *dst,
+                                 size_t dst_row_bytes, size_t dst_rows_per_ky, size_t width_bytes, int nzc, int kyl,
+                                 cudaStream_t st)
+{
+    cudaMemcpy3DParms p;
+    memset(&p, 0, sizeof(p));
+    p.srcPtr = make_cudaPitchedPtr(const_cast<void *>(src), src_row_bytes, width_bytes, src_rows_per_ky);
+    p.dstPtr = make_cudaPitchedPtr(dst, dst_row_bytes, width_bytes, dst_rows_per_ky);
+    p.extent = make_cudaExtent(width_bytes, (size_t)nzc, (size_t)kyl);
+    p.kind = cudaMemcpyDefault;
+    return cudaMemcpy3DAsync(&p, st);
+}
+
 static bool peers_ready(const EkSlabPoisson &S)
 {
     for (int i = 0; i < S.P; ++i)
@@ -351,6 +366,15 @@ ek_status ek_slab_poisson_push_x(ek_handle *h, int k)
     for (int i = 0; i < S.P; ++i) {
         p.src[i] = Ss + (size_t)i * S.kyl * nzc * S.NXl;                                      // rank i's ky rows
         p.dst[i] = reinterpret_cast<double2 *>(S.peerX[i]) + (size_t)za * S.NXg + (size_t)S.r * S.NXl;  // my columns there
+    }
+    if (S.dma) {
+        // start with my right-hand neighbour so that the ranks do not all write to the same peer at once
+        for (int j = 0; j < S.P; ++j) {
+            const int i = (S.r + 1 + j) % S.P;
+            EK_CUDA(h, copy_rows_dma(p.src[i], (size_t)S.NXl * 16, nzc, p.dst[i], (size_t)S.NXg * 16, S.M,
+                                     (size_t)S.NXl * 16, nzc, S.kyl, h->stream));
+        }
+        return EK_OK;
     }
     dim3 b(128), gr((S.NXl + 127) / 128, S.kyl * nzc, S.P);
     k_copy_rows<<<gr, b, 0, h->stream>>>(p, S.NXl, nzc, (long long)nzc * S.NXl, S.NXl, (long long)S.M * S.NXg, S.NXg);
@@ -375,10 +399,26 @@ ek_status ek_slab_poisson_push_back(ek_handle *h, int k)
         p.dst[i] = reinterpret_cast<double2 *>(S.peerR[i]) + (size_t)S.P * S.kyl * za * S.NXl
                    + (size_t)S.r * S.kyl * nzc * S.NXl;
     }
+    if (S.dma) {
+        for (int j = 0; j < S.P; ++j) {
+            const int i = (S.r + 1 + j) % S.P;
+            EK_CUDA(h, copy_rows_dma(p.src[i], (size_t)S.NXg * 16, S.M, p.dst[i], (size_t)S.NXl * 16, nzc,
+                                     (size_t)S.NXl * 16, nzc, S.kyl, h->stream));
+        }
+        return EK_OK;
+    }
     dim3 b(128), gr((S.NXl + 127) / 128, S.kyl * nzc, S.P);
     k_copy_rows<<<gr, b, 0, h->stream>>>(p, S.NXl, nzc, (long long)S.M * S.NXg, S.NXg, (long long)nzc * S.NXl, S.NXl);
     EK_CUDA(h, cudaGetLastError());
     h->poisson_launches += 1;
+    return EK_OK;
+}
+
+// 1: the peer-memory pushes use the copy engines (strided 3-D copies), 0: the re-blocking kernel
+ek_status ek_slab_poisson_set_dma(ek_handle *h, int on)
+{
+    if (!h) return EK_ERR_INVALID;
+    h->sp.dma = on != 0;
     return EK_OK;
 }
 

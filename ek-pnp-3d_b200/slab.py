@@ -133,6 +133,14 @@ class LocalComm:
     def stream_barrier(self):
         """cross-rank barrier in stream order: the slabs of this process share the stream"""
 
+    def stream_barrier_start(self):
+        ev = torch.cuda.Event()
+        ev.record()
+        return ev
+
+    def stream_barrier_finish(self, ev):
+        torch.cuda.current_stream().wait_event(ev)
+
     def map_peers(self, slabs) -> bool:
         """direct peer-memory transport: every slab gets the others' buffers as plain pointers"""
         ptrs = {}
@@ -204,6 +212,22 @@ class DistComm:
             if not hasattr(self, "_flag"):
                 self._flag = torch.zeros(1, dtype=torch.float32, device="cuda")
             self.dist.all_reduce(self._flag)
+
+    def stream_barrier_start(self):
+        """the same barrier, joined on the current stream and awaited (finish) on another one"""
+        if self.nranks == 1:
+            ev = torch.cuda.Event()
+            ev.record()
+            return ev
+        if not hasattr(self, "_flag"):
+            self._flag = torch.zeros(1, dtype=torch.float32, device="cuda")
+        return self.dist.all_reduce(self._flag, async_op=True)
+
+    def stream_barrier_finish(self, work):
+        if self.nranks == 1:
+            torch.cuda.current_stream().wait_event(work)
+        else:
+            work.wait()
 
     def map_peers(self, slabs) -> bool:
         """direct peer-memory transport: exchange CUDA IPC handles of the pencil and
@@ -331,6 +355,7 @@ class SlabGroup:
         self.K = 0
         self.side = torch.cuda.Stream(device=self.slabs[0].dev)
         self.halo_stream = torch.cuda.Stream(device=self.slabs[0].dev)
+        self.copy_stream = torch.cuda.Stream(device=self.slabs[0].dev)
         self.transport = "nccl"       # "nccl": all-to-all of the chunk buffers; "p2p": direct peer-memory writes
         self.set_poisson_chunks(4)
 
@@ -339,16 +364,20 @@ class SlabGroup:
         ks = {s.setup_poisson(nchunks) for s in self.slabs}
         assert len(ks) == 1
         self.K = ks.pop()
-        if self.transport == "p2p":
-            self.set_transport("p2p")     # the buffers were re-allocated: map them again
+        if self.transport != "nccl":
+            self.set_transport(self.transport)     # the buffers were re-allocated: map them again
 
     def set_transport(self, transport: str) -> str:
         """"p2p": the re-blocking kernels write straight into the peers' buffers over NVLink
-        (CUDA IPC); falls back to "nccl" when the buffers cannot be mapped"""
-        if transport == "p2p":
+        (CUDA IPC); "dma": the same pushes as strided copies on the copy engines; both fall
+        back to "nccl" when the buffers cannot be mapped"""
+        if transport in ("p2p", "dma"):
             self.comm.barrier()
-            transport = "p2p" if self.comm.map_peers(self.slabs) else "nccl"
+            if not self.comm.map_peers(self.slabs):
+                transport = "nccl"
             self.comm.barrier()
+        for s in self.slabs:
+            s.ck(s.L.ek_slab_poisson_set_dma(s.h, int(transport == "dma")), "ek_slab_poisson_set_dma")
         self.transport = transport
         return transport
 
@@ -409,7 +438,7 @@ class SlabGroup:
         """chunk k: re-blocking + y-transform of my columns, then its transpose starts"""
         for s in self.slabs:
             s.ck(s.L.ek_slab_poisson_forward(s.h, k), "ek_slab_poisson_forward")
-        if self.transport == "p2p":
+        if self.transport != "nccl":
             for s in self.slabs:
                 s.ck(s.L.ek_slab_poisson_push_x(s.h, k), "ek_slab_poisson_push_x")
             return None
@@ -417,7 +446,7 @@ class SlabGroup:
 
     def poisson_rest(self, pending):
         """everything after the forward halves were started: pencils, solve, way back"""
-        if self.transport == "p2p":
+        if self.transport != "nccl":
             return self._poisson_rest_p2p()
         for k, hnd in enumerate(pending):
             self._a2a_finish(hnd)
@@ -457,17 +486,23 @@ class SlabGroup:
         for s in self.slabs:
             s.ck(s.L.ek_slab_poisson_solve(s.h), "ek_slab_poisson_solve")
         self._mark("poisson_x_fft_zsolve_x_ifft")
+        # pushes of chunk k+1 travel (copy stream) while chunk k is transformed back (main
+        # stream); one barrier per chunk tells every rank that its x blocks have landed
+        main = torch.cuda.current_stream()
+        self.copy_stream.wait_stream(main)
+        landed = []
+        with self._on_stream(self.copy_stream):
+            for k in range(self.K):
+                for s in self.slabs:
+                    s.ck(s.L.ek_slab_poisson_push_back(s.h, k), "ek_slab_poisson_push_back")
+                landed.append(self.comm.stream_barrier_start())
         for k in range(self.K):
-            for s in self.slabs:
-                s.ck(s.L.ek_slab_poisson_push_back(s.h, k), "ek_slab_poisson_push_back")
-        self.comm.stream_barrier()            # every rank's x blocks have landed in my receive buffer
-        self._mark("poisson_transpose_2_push")
-        for k in range(self.K):
+            self.comm.stream_barrier_finish(landed[k])
             for s in self.slabs:
                 s.ck(s.L.ek_slab_poisson_backward(s.h, k), "ek_slab_poisson_backward")
         for s in self.slabs:
             s.ck(s.L.ek_poisson_finish(s.h, 0), "ek_poisson_finish")
-        self._mark("poisson_y_ifft")
+        self._mark("poisson_transpose_2_y_ifft")
         self.phi_halo_exchange()
         self._mark("phi_halo")
 
@@ -648,7 +683,8 @@ def bench_slabs(ek, dist, args, w, wl, local_rank):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": w["name"], "grid": [NX, NY, NZ], "stream_mode": "aa", "zchunk": args.zchunk,
                        "parallelism": f"x-slabs x{comm.nranks}: NCCL halo send/recv + Poisson transposes by "
-                                      + ("NCCL all-to-all, " if transport == "nccl" else "direct peer-memory writes (CUDA IPC), ") +
+                                      + {"nccl": "NCCL all-to-all, ", "p2p": "direct peer-memory writes (CUDA IPC, kernel), ",
+                                         "dma": "direct peer-memory copies (CUDA IPC, copy engines), "}[transport] +
                                       f"{grp.K} z-chunks, forward half overlapped with the LBM launches",
                        "cells_per_gpu": cells // comm.nranks, "init": "reference start-up (PB iterations) %.2f s" % init_s,
                        "l2": "per-GPU working set >> 126 MB L2", "phase_ms_rank0": phases},

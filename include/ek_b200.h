@@ -240,6 +240,8 @@ ek_status ek_slab_poisson_set_peer(ek_handle *h, int rank, void *X, void *R);
 ek_status ek_slab_poisson_my_buffers(ek_handle *h, void **X, void **R);
 ek_status ek_slab_poisson_push_x(ek_handle *h, int k);
 ek_status ek_slab_poisson_push_back(ek_handle *h, int k);
+/* pushes by strided 3-D copies on the copy engines (NVLink DMA, no SM time) instead of the kernel */
+ek_status ek_slab_poisson_set_dma(ek_handle *h, int on);
 /* the pieces of initialization() (LBM.cu:68-146) for a host-driven PB loop */
 ek_status ek_init_uniform(ek_handle *h);
 ek_status ek_pbe(ek_handle *h);
