@@ -129,6 +129,11 @@ def load_library():
     L.ek_max_uz.argtypes = [H, C.POINTER(C.c_double)]
     L.ek_save_data_tecplot.argtypes = [H, C.c_char_p, C.c_double, C.c_int, C.c_int]
     L.ek_save_data_end.argtypes = [H, C.c_char_p, C.c_double]
+    L.ek_read_data.argtypes = [H, C.c_char_p, C.POINTER(C.c_double)]
+    L.ek_checkpoint_save.argtypes = [H, C.c_char_p, C.c_double]
+    L.ek_checkpoint_load.argtypes = [H, C.c_char_p, C.POINTER(C.c_double)]
+    L.ek_set_populations.argtypes = [H, C.c_int, C.c_void_p]
+    L.ek_populations_restored.argtypes = [H]
     _lib = L
     return L
 
@@ -322,3 +327,22 @@ class Simulation:
     def save_data_end(self, path: str, time: float | None = None):
         self._ck(self.L.ek_save_data_end(self.h, path.encode(), self.t if time is None else time),
                  "ek_save_data_end")
+
+    # -- restart (LBM.cu:2629-2671) and exact checkpoints ------------------------
+    def read_data(self, path: str) -> float:
+        """read_data() of the reference: macroscopic arrays from a save_data_end file;
+        follow with init_equilibrium() as main.cu does"""
+        t = C.c_double()
+        self._ck(self.L.ek_read_data(self.h, path.encode(), C.byref(t)), "ek_read_data")
+        self.t = t.value
+        return t.value
+
+    def checkpoint_save(self, path: str, time: float | None = None):
+        self._ck(self.L.ek_checkpoint_save(self.h, path.encode(), self.t if time is None else time),
+                 "ek_checkpoint_save")
+
+    def checkpoint_load(self, path: str) -> float:
+        t = C.c_double()
+        self._ck(self.L.ek_checkpoint_load(self.h, path.encode(), C.byref(t)), "ek_checkpoint_load")
+        self.t = t.value
+        return t.value

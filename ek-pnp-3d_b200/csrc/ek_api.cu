@@ -580,4 +580,40 @@ ek_status ek_get_populations(ek_handle *h, int set, double *dst, int dst_on_devi
     return EK_OK;
 }
 
+// Restore one population set from host memory: (27, NZ, NY, NX) pre-collision values in the
+// reference's order, as ek_get_populations() returns them.  The lattice goes back to the
+// natural layout (A-A parity 0); call ek_populations_restored() after the four sets.
+ek_status ek_set_populations(ek_handle *h, int set, const double *src)
+{
+    if (!h || !src || set < 0 || set >= EK_NSETS) return EK_ERR_INVALID;
+    DeviceGuard g(h->device);
+    ek_status st = ek_alloc_state(h);
+    if (st != EK_OK) return st;
+    const size_t cells = (size_t)h->c.NX * h->c.NY * h->c.NZ;
+    h->cur = 0;
+    h->parity = 0;
+    StepArgs a = ek_step_args(h);
+    double *buf = nullptr;
+    EK_CUDA(h, cudaMalloc((void **)&buf, 27 * cells * sizeof(double)));
+    cudaError_t e = cudaMemcpyAsync(buf, src, 27 * cells * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = ek_launch_import(a, set, buf, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(buf);
+    EK_CUDA(h, e);
+    return EK_OK;
+}
+
+// the state machine after ek_set_fields() + 4 x ek_set_populations(): a run that continues
+ek_status ek_populations_restored(ek_handle *h)
+{
+    if (!h) return EK_ERR_INVALID;
+    if (!h->allocated || !h->fields_ready) { ek_set_error(h, "ek_populations_restored before the fields were set"); return EK_ERR_STATE; }
+    h->cur = 0;
+    h->parity = 0;
+    h->pops_ready = true;
+    h->e_from_arrays = false;   // E = -grad(phi) of the restored potential, as in the run that was saved
+    h->efield_stale = false;
+    return EK_OK;
+}
+
 }  // extern "C"

@@ -1,12 +1,14 @@
 // ek_io.cu -- diagnostics and field dumps in the reference's formats.
 //
 // Replaces current() (LBM.cu:2674-2710), the reduction of record_umax()
-// (LBM.cu:2712-2753), save_data_tecplot() (LBM.cu:2492-2565) and
-// save_data_end() (LBM.cu:2567-2627).  The diagnostics are device reductions
+// (LBM.cu:2712-2753), save_data_tecplot() (LBM.cu:2492-2565),
+// save_data_end() (LBM.cu:2567-2627) and read_data() (LBM.cu:2629-2671); adds an
+// exact binary checkpoint of the full state (the text restart keeps 6 decimals).  The diagnostics are device reductions
 // (the reference copies three full fields to the host for each); the dumps
 // keep the reference's text formats, including the dump-time linear
 // extrapolation of rho, c+, c-, u onto the wall planes (LBM.cu:2527-2542).
 #include <stdio.h>
+#include <string.h>
 
 #include <vector>
 
@@ -166,6 +168,118 @@ ek_status ek_save_data_end(ek_handle *h, const char *path, double time)
                 H.f[EK_UX][i], H.f[EK_UY][i], H.f[EK_UZ][i], H.f[EK_RHO][i], H.f[EK_CHARGE][i], H.f[EK_CHARGEN][i],
                 H.f[EK_PHI][i], H.f[EK_EX][i], H.f[EK_EY][i], H.f[EK_EZ][i], H.f[EK_T][i]);
     fclose(f);
+    return EK_OK;
+}
+
+// read_data() (LBM.cu:2629-2671): the text file written by save_data_end(), twelve
+// columns per cell in scalar_index order (time ux uy uz rho c+ c- phi Ex Ey Ez T).  As in
+// the reference the macroscopic arrays are restored and the caller re-creates the
+// populations with ek_init_equilibrium() (main.cu:161-176); E is taken from the file.
+ek_status ek_read_data(ek_handle *h, const char *path, double *time)
+{
+    if (!h || !path) return EK_ERR_INVALID;
+    FILE *f = fopen(path, "r");
+    if (!f) { ek_set_error(h, std::string("cannot open ") + path); return EK_ERR_INVALID; }
+    const size_t cells = (size_t)h->c.NX * h->c.NY * h->c.NZ;
+    HostFields H;
+    for (int k = 0; k < EK_NFIELDS; ++k) H.f[k].resize(cells);
+    double t = 0.0;
+    for (size_t i = 0; i < cells; ++i) {
+        const int n = fscanf(f, "%lf %lf %lf %lf %lf %lf %lf %lf %lf %lf %lf %lf", &t, &H.f[EK_UX][i], &H.f[EK_UY][i],
+                             &H.f[EK_UZ][i], &H.f[EK_RHO][i], &H.f[EK_CHARGE][i], &H.f[EK_CHARGEN][i], &H.f[EK_PHI][i],
+                             &H.f[EK_EX][i], &H.f[EK_EY][i], &H.f[EK_EZ][i], &H.f[EK_T][i]);
+        if (n != 12) {
+            fclose(f);
+            ek_set_error(h, std::string(path) + ": truncated or malformed restart file (cell " + std::to_string(i) + ")");
+            return EK_ERR_INVALID;
+        }
+    }
+    fclose(f);
+    const double *ptr[EK_NFIELDS];
+    for (int k = 0; k < EK_NFIELDS; ++k) ptr[k] = H.f[k].data();
+    ek_status st = ek_set_fields(h, ptr, 0);
+    if (st != EK_OK) return st;
+    if (time) *time = t;
+    return EK_OK;
+}
+
+// ---- exact binary checkpoint: header, 11 fields, c+ - c-, the four population sets in the
+// reference's natural order (27 x cells, pre-collision values) -- independent of the
+// in-place layout, the A-A parity and the slab/ghost padding of the run that wrote it.
+namespace {
+struct CkptHeader {
+    char magic[8];        // "EKB200C1"
+    int NX, NY, NZ, nfields;
+    long long steps;
+    double time;
+};
+}  // namespace
+
+ek_status ek_checkpoint_save(ek_handle *h, const char *path, double time)
+{
+    if (!h || !path) return EK_ERR_INVALID;
+    if (!h->pops_ready) { ek_set_error(h, "ek_checkpoint_save before the populations exist"); return EK_ERR_STATE; }
+    FILE *f = fopen(path, "wb");
+    if (!f) { ek_set_error(h, std::string("cannot open ") + path); return EK_ERR_INVALID; }
+    CkptHeader hd;
+    memcpy(hd.magic, "EKB200C1", 8);
+    hd.NX = h->c.NX; hd.NY = h->c.NY; hd.NZ = h->c.NZ; hd.nfields = EK_NFIELDS;
+    hd.steps = h->steps; hd.time = time;
+    bool ok = fwrite(&hd, sizeof(hd), 1, f) == 1;
+    const size_t cells = (size_t)h->c.NX * h->c.NY * h->c.NZ;
+    std::vector<double> buf(cells * 27);
+    ek_status st = EK_OK;
+    for (int k = 0; k < EK_NFIELDS && ok && st == EK_OK; ++k) {
+        st = ek_get_field(h, k, buf.data(), 0);
+        ok = st == EK_OK && fwrite(buf.data(), sizeof(double), cells, f) == cells;
+    }
+    for (int s = 0; s < 4 && ok && st == EK_OK; ++s) {
+        st = ek_get_populations(h, s, buf.data(), 0);
+        ok = st == EK_OK && fwrite(buf.data(), sizeof(double), cells * 27, f) == cells * 27;
+    }
+    fclose(f);
+    if (st != EK_OK) return st;
+    if (!ok) { ek_set_error(h, std::string("short write to ") + path); return EK_ERR_INVALID; }
+    return EK_OK;
+}
+
+ek_status ek_checkpoint_load(ek_handle *h, const char *path, double *time)
+{
+    if (!h || !path) return EK_ERR_INVALID;
+    FILE *f = fopen(path, "rb");
+    if (!f) { ek_set_error(h, std::string("cannot open ") + path); return EK_ERR_INVALID; }
+    CkptHeader hd;
+    if (fread(&hd, sizeof(hd), 1, f) != 1 || memcmp(hd.magic, "EKB200C1", 8) != 0 || hd.NX != h->c.NX ||
+        hd.NY != h->c.NY || hd.NZ != h->c.NZ || hd.nfields != EK_NFIELDS) {
+        fclose(f);
+        ek_set_error(h, std::string(path) + ": not a checkpoint of this grid");
+        return EK_ERR_INVALID;
+    }
+    const size_t cells = (size_t)h->c.NX * h->c.NY * h->c.NZ;
+    HostFields H;
+    bool ok = true;
+    for (int k = 0; k < EK_NFIELDS && ok; ++k) {
+        H.f[k].resize(cells);
+        ok = fread(H.f[k].data(), sizeof(double), cells, f) == cells;
+    }
+    ek_status st = EK_OK;
+    if (ok) {
+        const double *ptr[EK_NFIELDS];
+        for (int k = 0; k < EK_NFIELDS; ++k) ptr[k] = H.f[k].data();
+        st = ek_set_fields(h, ptr, 0);
+    }
+    std::vector<double> buf(cells * 27);
+    for (int s = 0; s < 4 && ok && st == EK_OK; ++s) {
+        ok = fread(buf.data(), sizeof(double), cells * 27, f) == cells * 27;
+        if (ok) st = ek_set_populations(h, s, buf.data());
+    }
+    fclose(f);
+    if (st != EK_OK) return st;
+    if (!ok) { ek_set_error(h, std::string(path) + ": truncated checkpoint"); return EK_ERR_INVALID; }
+    st = ek_populations_restored(h);
+    if (st != EK_OK) return st;
+    h->steps = hd.steps;
+    if (time) *time = hd.time;
     return EK_OK;
 }
 

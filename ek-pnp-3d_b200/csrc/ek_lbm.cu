@@ -553,6 +553,29 @@ __global__ void ek_export_kernel(const StepArgs a, int s, double *dst)
     for (int d = 0; d < 27; ++d) dst[(size_t)d * cells + o] = S[d];
 }
 
+// the inverse of the export for the natural layout (A-A parity 0 / current push lattice):
+// restores a checkpointed pre-collision state, wall-node side buffers included
+__global__ void ek_import_kernel(const StepArgs a, int s, const double *src)
+{
+    const EkConst &c = a.c;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= c.NX) return;
+    const int y = blockIdx.y, z = blockIdx.z;
+    const size_t cells = (size_t)c.NX * c.NY * c.NZ;
+    const size_t o = (size_t)c.NX * ((size_t)c.NY * z + y) + x;
+    const bool wall = (z == 0 || z == c.NZ - 1);
+    double *lat = a.in[s] + (size_t)z * c.lplane + (size_t)y * c.lrow + ek_lat_col(x);
+    double *Wn = nullptr;
+    if (s > 0 && wall)
+        Wn = a.wall + (size_t)(s - 1) * 2 * 27 * c.plane + (size_t)(z == 0 ? 0 : 27) * c.plane + y * c.PX + x;
+#pragma unroll
+    for (int d = 0; d < 27; ++d) {
+        const double v = src[(size_t)d * cells + o];
+        lat[(size_t)d * EK_TILE] = v;
+        if (Wn) Wn[(size_t)d * c.plane] = v;
+    }
+}
+
 template <int MODE>
 cudaError_t launch_mode5(const StepArgs &a, bool full, bool earr, dim3 grid, cudaStream_t st)
 {
@@ -613,5 +636,13 @@ cudaError_t ek_launch_export(const StepArgs &a, int mode, int set, double *dst, 
     dim3 block(64), grid((c.NX + 63) / 64, c.NY, c.NZ);
     if (mode == EK_MODE_AA_ODD) ek_export_kernel<EK_MODE_AA_ODD><<<grid, block, 0, st>>>(a, set, dst);
     else ek_export_kernel<EK_MODE_AA_EVEN><<<grid, block, 0, st>>>(a, set, dst);
+    return cudaGetLastError();
+}
+
+cudaError_t ek_launch_import(const StepArgs &a, int set, const double *src, cudaStream_t st)
+{
+    const EkConst &c = a.c;
+    dim3 block(64), grid((c.NX + 63) / 64, c.NY, c.NZ);
+    ek_import_kernel<<<grid, block, 0, st>>>(a, set, src);
     return cudaGetLastError();
 }

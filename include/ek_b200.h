@@ -171,6 +171,16 @@ ek_status ek_max_uz(ek_handle *h, double *umax);
  * VARIABLES header. */
 ek_status ek_save_data_tecplot(ek_handle *h, const char *path, double time, int append, int first);
 ek_status ek_save_data_end(ek_handle *h, const char *path, double time);
+/* Restart.  ek_read_data = read_data() (LBM.cu:2629-2671): restores the macroscopic
+ * arrays from the text file of save_data_end (6 decimals, as the reference); the
+ * caller then calls ek_init_equilibrium() like main.cu:161-176.  The checkpoint pair
+ * is the lossless alternative: fields and pre-collision populations in the
+ * reference's natural order, independent of the in-place layout and A-A parity. */
+ek_status ek_read_data(ek_handle *h, const char *path, double *time);
+ek_status ek_checkpoint_save(ek_handle *h, const char *path, double time);
+ek_status ek_checkpoint_load(ek_handle *h, const char *path, double *time);
+ek_status ek_set_populations(ek_handle *h, int set, const double *host_src);
+ek_status ek_populations_restored(ek_handle *h);
 
 /* ------------------------------------------------------------------------
  * Multi-GPU: x-slab decomposition (new; the reference is single-GPU,

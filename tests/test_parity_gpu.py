@@ -488,3 +488,66 @@ def test_c2_slit_flow_matches_the_analytic_profiles(ek):
     assert np.abs(ux[inner] - mob * (phi[inner] - phi_slip)).max() <= 1e-2 * u_scale
     phi_slip_dh = zeta * np.cosh(kappa * (0.5 * p.dz - 0.5 * H)) / np.cosh(0.5 * kappa * H)
     assert np.abs(ux[inner] - mob * (phi_dh[inner] - phi_slip_dh)).max() <= 1e-2 * u_scale
+
+
+# ---------------------------------------------------------------------------
+# restart: read_data() text format and the exact checkpoint
+# ---------------------------------------------------------------------------
+def test_checkpoint_continues_bit_for_bit(ek, tmp_path):
+    """save after 5 steps (A-A parity 1), load into a fresh handle (natural layout, either
+    streaming scheme), continue 4 steps: identical to the uninterrupted 9-step run"""
+    over = dict(NX=40, NY=5, NZ=13, uw=1.0e-4, exf=1.0e6)
+    init = synthetic_init(over)
+    sim = ek.Simulation(ek.default_params(**over))
+    sim.set_fields(init)
+    sim.init_equilibrium()
+    sim.step(5)
+    path = str(tmp_path / "state.ekc")
+    sim.checkpoint_save(path)
+    sim.step(4)
+    want_f, want_p = sim.fields(), np.stack([sim.populations(s) for s in range(4)])
+    sim.close()
+    for mode in (ek.STREAM_AA, ek.STREAM_PUSH):
+        sim = ek.Simulation(ek.default_params(**over), stream_mode=mode)
+        t = sim.checkpoint_load(path)
+        assert abs(t - 5 * sim.p.dt) <= 1e-20
+        sim.step(4)
+        got_f, got_p = sim.fields(), np.stack([sim.populations(s) for s in range(4)])
+        sim.close()
+        for k in util.FIELDS:
+            assert np.array_equal(got_f[k], want_f[k]), (mode, k)
+        assert np.array_equal(got_p, want_p), mode
+    # a checkpoint of another grid is refused
+    sim = ek.Simulation(ek.default_params(NX=40, NY=5, NZ=15))
+    with pytest.raises(ek.EkError):
+        sim.checkpoint_load(path)
+    sim.close()
+
+
+def test_read_data_restores_the_reference_text_restart(ek, tmp_path):
+    """save_data_end() -> read_data() (LBM.cu:2567-2671): the file keeps six decimals and the
+    dump-time wall extrapolation, so the restored arrays equal the dumped ones to 5e-7 absolute"""
+    over = dict(NX=12, NY=4, NZ=9)
+    sim = ek.Simulation(ek.default_params(**dict(over, pb_iters=30)))
+    sim.init()
+    sim.step(3)
+    path = str(tmp_path / "data_end.dat")
+    sim.save_data_end(path, 3.0e-10)
+    dumped = sim.fields()
+    sim.close()
+    sim = ek.Simulation(ek.default_params(**over))
+    t = sim.read_data(path)
+    assert abs(t - 0.0) <= 5e-7          # "%10.6f" of 3e-10
+    got = sim.fields()
+    sim.init_equilibrium()               # main.cu:174 -- the restart re-creates the populations
+    sim.step(1)
+    sim.close()
+    for k in ("phi", "T", "Ex", "Ey", "Ez"):
+        assert np.abs(got[k] - dumped[k]).max() <= 5.1e-7, k
+    for k in ("rho", "charge", "chargen", "ux", "uy", "uz"):
+        a = dumped[k].copy()                                  # LBM.cu:2598-2613
+        a[0] = 2.0 * a[1] - a[2]
+        a[-1] = 2.0 * a[-2] - a[-3]
+        assert np.abs(got[k] - a).max() <= 5.1e-7, k
+    with pytest.raises(ek.EkError):
+        ek.Simulation(ek.default_params(NX=12, NY=4, NZ=11)).read_data(path)   # too few cells
