@@ -212,7 +212,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, help="c1|c2|c3|c4 (default c3 at N=1, c4 at N>1)")
     ap.add_argument("--stream-mode", default="aa", choices=["aa", "push"])
-    ap.add_argument("--zchunk", type=int, default=32)
+    ap.add_argument("--zchunk", type=int, default=None, help="z-planes per CTA of the LBM kernel (default: automatic)")
     ap.add_argument("--ref-all", action="store_true", help="reference arm: try every nThreads variant")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel", type=int, default=None, help="LBM kernel variant (ek_set_option kernel)")
@@ -273,6 +273,7 @@ def main():
     sim = ek.Simulation(p, device=local_rank, stream_mode=mode, zchunk=args.zchunk)
     if args.kernel is not None:
         sim.set_option("kernel", args.kernel)
+    zchunk_used = int(sim.counter("zchunk"))
     t0 = time.time()
     sim.init()            # the reference's start-up: 501 Poisson-Boltzmann iterations + equilibrium
     sim.sync()
@@ -343,7 +344,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": w["name"], "grid": [NX, NY, NZ], "stream_mode": args.stream_mode,
-                       "zchunk": args.zchunk, "init": "reference start-up (501 PB iterations) %.2f s" % init_s,
+                       "zchunk": zchunk_used, "init": "reference start-up (501 PB iterations) %.2f s" % init_s,
                        "l2": "working set 14.5 GB of populations per step >> 126 MB L2 (no flush needed)",
                        "parallelism": "1 GPU"},
             "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,

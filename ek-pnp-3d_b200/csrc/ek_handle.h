@@ -46,7 +46,7 @@ struct ek_handle {
     bool e_from_arrays = false;    // next LBM pass takes E from the arrays, not from grad(phi)
     bool efield_stale = false;     // Ex/Ey/Ez arrays are older than phi (recomputed on demand)
     bool phi_walls_dirty = true;   // something other than the solver wrote phi: its wall planes must be re-imposed
-    int zchunk = 32;
+    int zchunk = 16;               // z-planes per CTA (ek_auto_zchunk at creation; option "zchunk")
     int kernel = 0;                // 0 = four warps + lean interior path, 1 = eight warps, 2 = five warps, 3 = four warps, general path only
     int dc_mode = EK_DC_ZERO;
     int poisson_path = 0;          // 0: xy-FFT + tridiagonal z-solve, 1: odd-extension 3-D FFT
@@ -62,5 +62,6 @@ struct ek_handle {
 };
 
 void ek_compute_consts(const ek_params &p, EkConst &c, bool slab);
+int ek_auto_zchunk(const EkConst &c);
 ek_status ek_alloc_state(ek_handle *h);
 StepArgs ek_step_args(ek_handle *h);

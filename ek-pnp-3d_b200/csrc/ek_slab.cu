@@ -75,6 +75,7 @@ ek_status ek_create_slab(const ek_params *global, int device, int rank, int nran
     h->NXg = global->NX;
     h->stream_mode = EK_STREAM_AA;
     ek_compute_consts(local, h->c, true);
+    h->zchunk = ek_auto_zchunk(h->c);
     *out = h;
     return EK_OK;
 }

@@ -681,7 +681,7 @@ def bench_slabs(ek, dist, args, w, wl, local_rank):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4),
             "higher_is_better": True, "scaling": "weak" if w.get("weak") else "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": w["name"], "grid": [NX, NY, NZ], "stream_mode": "aa", "zchunk": args.zchunk,
+            "config": {"workload": w["name"], "grid": [NX, NY, NZ], "stream_mode": "aa", "zchunk": int(grp.slabs[0].sim.counter("zchunk")),
                        "parallelism": f"x-slabs x{comm.nranks}: NCCL halo send/recv + Poisson transposes by "
                                       + {"nccl": "NCCL all-to-all, ", "p2p": "direct peer-memory writes (CUDA IPC, kernel), ",
                                          "dma": "direct peer-memory copies (CUDA IPC, copy engines), "}[transport] +

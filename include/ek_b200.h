@@ -151,7 +151,7 @@ ek_status ek_set_poisson_dc(ek_handle *h, int mode, double ghat0);
  * reference's odd-extension 3-D FFT), "profile" (1: time every LBM/Poisson
  * launch with CUDA events). */
 ek_status ek_set_option(ek_handle *h, const char *key, long long value);
-/* counters: "steps", "lbm_launches", "poisson_launches", "kernel_launches";
+/* counters: "steps", "zchunk", "lbm_launches", "poisson_launches", "kernel_launches";
  * times (ms, profile on): "lbm_ms", "poisson_ms" */
 ek_status ek_get_counter(ek_handle *h, const char *key, double *value);
 ek_status ek_reset_counters(ek_handle *h);
