@@ -381,8 +381,11 @@ __device__ __forceinline__ void fluid_role(const StepArgs &a, Sh &sh, const int 
 }
 
 // LEAN: deep-interior planes take the lean node path (A-A modes only)
+#ifndef EK_MIN_CTAS
+#define EK_MIN_CTAS 4   // 128 registers; 3 (168 registers, no rematerialisation) measured slower, DESIGN.md 3.6
+#endif
 template <int MODE, bool FULL, bool EARR, bool LEAN>
-__global__ void __launch_bounds__(128, 4) ek_step_kernel(const __grid_constant__ StepArgs a)
+__global__ void __launch_bounds__(128, EK_MIN_CTAS) ek_step_kernel(const __grid_constant__ StepArgs a)
 {
     __shared__ Sh sh;
     const EkConst &c = a.c;

@@ -48,6 +48,20 @@ __device__ __forceinline__ size_t dq_at(const EkConst &c, const Nbr &nb, int z)
     return (size_t)z * c.dq_sz + (size_t)nb.yy * c.dq_sy + nb.fx[1];
 }
 
+// population loads/stores.  The lattice is streamed once per step (no reuse inside a launch):
+// EK_LD/EK_ST select the cache operator (default: plain; -DEK_CACHE_CS: evict-first streaming,
+// -DEK_CACHE_CG: L2 only) -- measured variants are recorded in DESIGN.md 3.6.
+#if defined(EK_CACHE_CS)
+#define EK_LD(p) __ldcs(p)
+#define EK_ST(p, v) __stcs((p), (v))
+#elif defined(EK_CACHE_CG)
+#define EK_LD(p) __ldcg(p)
+#define EK_ST(p, v) __stcg((p), (v))
+#else
+#define EK_LD(p) (*(p))
+#define EK_ST(p, v) (*(p) = (v))
+#endif
+
 // pre-collision populations of a node ("pull" restatement)
 template <int MODE>
 __device__ __forceinline__ void gather27(const double *lat, const Nbr &nb, double S[27])
@@ -56,12 +70,12 @@ __device__ __forceinline__ void gather27(const double *lat, const Nbr &nb, doubl
 #pragma unroll
         for (int d = 0; d < 27; ++d) {
             const double *q = lat + nb.at(-ek_cx(d), -ek_cy(d), -ek_cz(d));
-            S[d] = q[ek_opp(d) * EK_TILE];
+            S[d] = EK_LD(q + ek_opp(d) * EK_TILE);
         }
     } else {
         const double *q = lat + nb.lc();
 #pragma unroll
-        for (int d = 0; d < 27; ++d) S[d] = q[d * EK_TILE];
+        for (int d = 0; d < 27; ++d) S[d] = EK_LD(q + d * EK_TILE);
     }
 }
 
@@ -71,10 +85,10 @@ __device__ __forceinline__ void put(double *lat, const Nbr &nb, double v)
 {
     if (MODE == EK_MODE_AA_EVEN) {
         double *q = lat + nb.lc();
-        q[ek_opp(d) * EK_TILE] = v;
+        EK_ST(q + ek_opp(d) * EK_TILE, v);
     } else {
         double *q = lat + nb.at(ek_cx(d), ek_cy(d), ek_cz(d));
-        q[d * EK_TILE] = v;
+        EK_ST(q + d * EK_TILE, v);
     }
 }
 
@@ -177,12 +191,12 @@ __device__ __forceinline__ void gather27_lean(const LeanAddr &la, double S[27])
 #pragma unroll
         for (int d = 0; d < 27; ++d) {
             const double *q = lean_ptr(la.b[1 - ek_cz(d)], la.oxy[1 - ek_cy(d)][1 - ek_cx(d)]);
-            S[d] = q[ek_opp(d) * EK_TILE];
+            S[d] = EK_LD(q + ek_opp(d) * EK_TILE);
         }
     } else {
         const double *q = lean_ptr(la.b[1], la.oxy[1][1]);
 #pragma unroll
-        for (int d = 0; d < 27; ++d) S[d] = q[d * EK_TILE];
+        for (int d = 0; d < 27; ++d) S[d] = EK_LD(q + d * EK_TILE);
     }
 }
 
@@ -192,10 +206,10 @@ __device__ __forceinline__ void putx(double *lat, const Nbr &nb, const LeanAddr 
     if (LEAN) {
         if (MODE == EK_MODE_AA_EVEN) {
             double *q = lean_ptr(la.b[1], la.oxy[1][1]);
-            q[ek_opp(d) * EK_TILE] = v;
+            EK_ST(q + ek_opp(d) * EK_TILE, v);
         } else {
             double *q = lean_ptr(la.b[1 + ek_cz(d)], la.oxy[1 + ek_cy(d)][1 + ek_cx(d)]);
-            q[d * EK_TILE] = v;
+            EK_ST(q + d * EK_TILE, v);
         }
     } else {
         put<MODE, d>(lat, nb, v);

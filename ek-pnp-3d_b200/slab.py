@@ -675,13 +675,40 @@ def bench_slabs(ek, dist, args, w, wl, local_rank):
     grp.profile = True
     grp.step(max(4, args.warmup))
     phases = {k: round(v / max(4, args.warmup), 4) for k, v in grp.phase_times().items()}
+    grp.profile = False
+    zchunk_used = int(grp.slabs[0].sim.counter("zchunk"))
+    # ---- end to end through the C ABI with HOST buffers: every rank uploads its slab of the 11
+    # macroscopic arrays from pinned memory, init_equilibrium, K steps, downloads the 11 arrays
+    e2e = None
+    if not getattr(args, "no_e2e", False):
+        try:
+            sim = grp.slabs[0].sim
+            host = {n: torch.empty(sim.shape, dtype=torch.float64, pin_memory=True).numpy() for n in ek.FIELDS}
+            for n in ek.FIELDS:
+                sim.field(n, out=host[n])
+            comm.barrier()
+            t0 = time.perf_counter()
+            sim.set_fields(host)
+            grp.init_equilibrium()
+            grp.step(args.steps)
+            for n in ek.FIELDS:
+                sim.field(n, out=host[n])
+            torch.cuda.synchronize()
+            dt = comm.max_over_ranks(time.perf_counter() - t0)
+            e2e = {"value": round(cells * args.steps / dt / 1e6, 2), "unit": "MLUPS",
+                   "h2d_bytes_per_step": int(11 * cells * 8 / args.steps), "d2h_bytes_per_step": int(11 * cells * 8 / args.steps),
+                   "job": f"every rank: upload its slab of 11 fields (pinned host) + init_equilibrium + {args.steps} steps + "
+                          "download 11 fields; wall clock, max over ranks", "seconds": round(dt, 4)}
+            del host
+        except Exception as exc:  # noqa: BLE001  (e.g. the pinned allocation of 11 x 1 GB per rank failed)
+            e2e = {"value": None, "unit": "MLUPS", "error": str(exc)[:200]}
     grp.close()
     step_gbs = mlups * 1e6 * B_ALG_STEP / 1e9
     return {"metric": "coupled_step_mlups", "value": round(mlups, 2), "unit": "MLUPS", "n_gpus": comm.nranks,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4),
             "higher_is_better": True, "scaling": "weak" if w.get("weak") else "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": w["name"], "grid": [NX, NY, NZ], "stream_mode": "aa", "zchunk": int(grp.slabs[0].sim.counter("zchunk")),
+            "config": {"workload": w["name"], "grid": [NX, NY, NZ], "stream_mode": "aa", "zchunk": zchunk_used,
                        "parallelism": f"x-slabs x{comm.nranks}: NCCL halo send/recv + Poisson transposes by "
                                       + {"nccl": "NCCL all-to-all, ", "p2p": "direct peer-memory writes (CUDA IPC, kernel), ",
                                          "dma": "direct peer-memory copies (CUDA IPC, copy engines), "}[transport] +
@@ -693,5 +720,5 @@ def bench_slabs(ek, dist, args, w, wl, local_rank):
                          "note": "whole coupled step per GPU at 1760 B/cell (kernel split is reported at N=1)",
                          "traffic": None},
             "cpu_baseline": None,
-            "e2e": None, "gpu_launches": launches, "clocks": clocks,
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "hbm_gbs_step": round(step_gbs, 1)}
