@@ -104,6 +104,8 @@ def load_library():
     L.ek_halo_unpack.argtypes = [H, C.c_int, C.c_void_p, C.c_void_p]
     L.ek_phi_halo_pack.argtypes = [H, C.c_void_p, C.c_void_p]
     L.ek_phi_halo_unpack.argtypes = [H, C.c_void_p, C.c_void_p]
+    L.ek_phi_halo_pack_range.argtypes = [H, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.ek_phi_halo_unpack_range.argtypes = [H, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.ek_dq_ptr.argtypes = [H, C.POINTER(C.c_void_p)]
     L.ek_zsolve_columns.argtypes = [H, C.c_void_p, C.c_int, C.c_int]
     L.ek_poisson_finish.argtypes = [H, C.c_int]

@@ -39,11 +39,11 @@ __global__ void k_halo_column(EkConst c, Lat4 lat, int col, int plus, double *bu
 }
 
 template <bool PACK>
-__global__ void k_phi_column(EkConst c, double *phi, int col, double *buf)
+__global__ void k_phi_column(EkConst c, double *phi, int col, double *buf, int z0)
 {
     const int y = blockIdx.x * blockDim.x + threadIdx.x;
     if (y >= c.NY) return;
-    const int z = blockIdx.y;
+    const int z = z0 + blockIdx.y;
     double *q = phi + (size_t)z * c.plane + (size_t)y * c.PX + col;
     double *b = buf + (size_t)z * c.NY + y;
     if (PACK) *b = *q; else *q = *b;
@@ -144,28 +144,40 @@ ek_status ek_halo_unpack(ek_handle *h, int phase, const double *from_left, const
 
 // phi: my first column goes to the left neighbour's right ghost, my last column
 // to the right neighbour's left ghost (NY*NZ doubles each)
-ek_status ek_phi_halo_pack(ek_handle *h, double *to_left, double *to_right)
+ek_status ek_phi_halo_pack_range(ek_handle *h, int z0, int z1, double *to_left, double *to_right)
 {
     if (!h || !h->slab || !h->allocated) return EK_ERR_STATE;
+    if (z0 < 0 || z1 > h->c.NZ || z1 <= z0) return EK_ERR_INVALID;
     DeviceGuard g(h->device);
     const EkConst &c = h->c;
-    dim3 b(128), gr((c.NY + 127) / 128, c.NZ);
-    k_phi_column<true><<<gr, b, 0, h->stream>>>(c, h->fld[EK_PHI], 0, to_left);
-    k_phi_column<true><<<gr, b, 0, h->stream>>>(c, h->fld[EK_PHI], c.NX - 1, to_right);
+    dim3 b(128), gr((c.NY + 127) / 128, z1 - z0);
+    k_phi_column<true><<<gr, b, 0, h->stream>>>(c, h->fld[EK_PHI], 0, to_left, z0);
+    k_phi_column<true><<<gr, b, 0, h->stream>>>(c, h->fld[EK_PHI], c.NX - 1, to_right, z0);
     EK_CUDA(h, cudaGetLastError());
     return EK_OK;
 }
 
-ek_status ek_phi_halo_unpack(ek_handle *h, const double *from_left, const double *from_right)
+ek_status ek_phi_halo_unpack_range(ek_handle *h, int z0, int z1, const double *from_left, const double *from_right)
 {
     if (!h || !h->slab || !h->allocated) return EK_ERR_STATE;
+    if (z0 < 0 || z1 > h->c.NZ || z1 <= z0) return EK_ERR_INVALID;
     DeviceGuard g(h->device);
     const EkConst &c = h->c;
-    dim3 b(128), gr((c.NY + 127) / 128, c.NZ);
-    k_phi_column<false><<<gr, b, 0, h->stream>>>(c, h->fld[EK_PHI], c.xlo, const_cast<double *>(from_left));
-    k_phi_column<false><<<gr, b, 0, h->stream>>>(c, h->fld[EK_PHI], c.xhi, const_cast<double *>(from_right));
+    dim3 b(128), gr((c.NY + 127) / 128, z1 - z0);
+    k_phi_column<false><<<gr, b, 0, h->stream>>>(c, h->fld[EK_PHI], c.xlo, const_cast<double *>(from_left), z0);
+    k_phi_column<false><<<gr, b, 0, h->stream>>>(c, h->fld[EK_PHI], c.xhi, const_cast<double *>(from_right), z0);
     EK_CUDA(h, cudaGetLastError());
     return EK_OK;
+}
+
+ek_status ek_phi_halo_pack(ek_handle *h, double *to_left, double *to_right)
+{
+    return h ? ek_phi_halo_pack_range(h, 0, h->c.NZ, to_left, to_right) : EK_ERR_INVALID;
+}
+
+ek_status ek_phi_halo_unpack(ek_handle *h, const double *from_left, const double *from_right)
+{
+    return h ? ek_phi_halo_unpack_range(h, 0, h->c.NZ, from_left, from_right) : EK_ERR_INVALID;
 }
 
 ek_status ek_dq_ptr(ek_handle *h, double **p)

@@ -352,10 +352,13 @@ class SlabGroup:
         self.profile = False          # per-phase CUDA-event timing (development aid)
         self._ev = []
         self.overlap = True           # forward half of the Poisson stage runs behind the LBM launches
+        self.overlap_back = True      # ... and the way back behind the next step's first LBM launches
         self.K = 0
         self.side = torch.cuda.Stream(device=self.slabs[0].dev)
         self.halo_stream = torch.cuda.Stream(device=self.slabs[0].dev)
         self.copy_stream = torch.cuda.Stream(device=self.slabs[0].dev)
+        self.back_stream = torch.cuda.Stream(device=self.slabs[0].dev)
+        self._phi_ready = None        # per-chunk events of the previous step's way back (overlapped steps)
         self.transport = "nccl"       # "nccl": all-to-all of the chunk buffers; "p2p": direct peer-memory writes
         self.set_poisson_chunks(4)
 
@@ -424,6 +427,51 @@ class SlabGroup:
         for s in self.slabs:
             s.ck(s.L.ek_phi_halo_unpack(s.h, C.c_void_p(s.p_from_l.data_ptr()), C.c_void_p(s.p_from_r.data_ptr())), "ek_phi_halo_unpack")
 
+    def phi_halo_exchange_range(self, z0: int, z1: int):
+        """ghost columns of phi for the planes [z0, z1) (contiguous slices of the halo buffers)"""
+        for s in self.slabs:
+            s.ck(s.L.ek_phi_halo_pack_range(s.h, z0, z1, C.c_void_p(s.p_to_l.data_ptr()), C.c_void_p(s.p_to_r.data_ptr())),
+                 "ek_phi_halo_pack_range")
+        a, b = z0 * self.slabs[0].NY, z1 * self.slabs[0].NY
+        self.comm.neighbor_exchange([s.p_to_l[a:b] for s in self.slabs], [s.p_to_r[a:b] for s in self.slabs],
+                                    [s.p_from_l[a:b] for s in self.slabs], [s.p_from_r[a:b] for s in self.slabs])
+        for s in self.slabs:
+            s.ck(s.L.ek_phi_halo_unpack_range(s.h, z0, z1, C.c_void_p(s.p_from_l.data_ptr()),
+                                              C.c_void_p(s.p_from_r.data_ptr())), "ek_phi_halo_unpack_range")
+
+    def _chunk_planes(self, k: int):
+        """planes of chunk k, wall planes included in the first and last chunk"""
+        zc = int(self.slabs[0].sim.counter("zchunk")) if not hasattr(self, "_zc") else self._zc
+        self._zc = zc
+        b0, b1 = self.slabs[0].blocks[k]
+        return b0 * zc, min(b1 * zc, self.slabs[0].NZ)
+
+    def _poisson_tail(self, landed, finish):
+        """way back, chunk by chunk on the `back` stream: wait until chunk k has landed, inverse
+        y-transform into phi, ghost columns of its planes, then the event that the next LBM
+        launches wait for.  The caller decides when the main stream joins (self.join_back())."""
+        main = torch.cuda.current_stream()
+        self.back_stream.wait_stream(main)
+        self._phi_ready = []
+        with self._on_stream(self.back_stream):
+            for k in range(self.K):
+                finish(landed[k])
+                for s in self.slabs:
+                    s.ck(s.L.ek_slab_poisson_backward(s.h, k), "ek_slab_poisson_backward")
+                if k == self.K - 1:
+                    for s in self.slabs:
+                        s.ck(s.L.ek_poisson_finish(s.h, 0), "ek_poisson_finish")
+                z0, z1 = self._chunk_planes(k)
+                self.phi_halo_exchange_range(z0, z1)
+                ev = torch.cuda.Event()
+                ev.record()
+                self._phi_ready.append(ev)
+
+    def join_back(self):
+        """the main stream waits for the whole potential (end of a step() call, start-up loop)"""
+        torch.cuda.current_stream().wait_stream(self.back_stream)
+        self._phi_ready = None
+
     def _a2a_start(self, k, which):
         bufs = [(s.send[k], s.recv[k]) for s in self.slabs]
         if bufs[0][0] is None:
@@ -462,15 +510,7 @@ class SlabGroup:
                 s.ck(s.L.ek_slab_poisson_scatter_x(s.h, k), "ek_slab_poisson_scatter_x")
             pending.append(self._a2a_start(k, 1))
         self._mark("poisson_scatter_x")
-        for k, hnd in enumerate(pending):
-            self._a2a_finish(hnd)
-            for s in self.slabs:
-                s.ck(s.L.ek_slab_poisson_backward(s.h, k), "ek_slab_poisson_backward")
-        for s in self.slabs:
-            s.ck(s.L.ek_poisson_finish(s.h, 0), "ek_poisson_finish")
-        self._mark("poisson_transpose_2_y_ifft")
-        self.phi_halo_exchange()
-        self._mark("phi_halo")
+        self._poisson_tail(pending, self._a2a_finish)
 
     def poisson_reference(self):
         """the same stage through torch.fft and un-chunked transposes (tests only)"""
@@ -496,15 +536,7 @@ class SlabGroup:
                 for s in self.slabs:
                     s.ck(s.L.ek_slab_poisson_push_back(s.h, k), "ek_slab_poisson_push_back")
                 landed.append(self.comm.stream_barrier_start())
-        for k in range(self.K):
-            self.comm.stream_barrier_finish(landed[k])
-            for s in self.slabs:
-                s.ck(s.L.ek_slab_poisson_backward(s.h, k), "ek_slab_poisson_backward")
-        for s in self.slabs:
-            s.ck(s.L.ek_poisson_finish(s.h, 0), "ek_poisson_finish")
-        self._mark("poisson_transpose_2_y_ifft")
-        self.phi_halo_exchange()
-        self._mark("phi_halo")
+        self._poisson_tail(landed, self.comm.stream_barrier_finish)
 
     def poisson(self):
         """the distributed fast_Poisson(): dq -> phi (interior, walls, ghost columns).
@@ -513,6 +545,8 @@ class SlabGroup:
         pending = [self.poisson_forward(k) for k in range(self.K)]
         self._mark("poisson_y_fft")
         self.poisson_rest(pending)
+        self.join_back()
+        self._mark("poisson_way_back")
 
     # -- the reference's call sequence ---------------------------------------------
     def initialization(self):
@@ -575,6 +609,10 @@ class SlabGroup:
         pending = []
         for k in range(self.K):
             b0, b1 = self.slabs[0].blocks[k]
+            if self._phi_ready is not None:
+                # the planes of chunk k take grad(phi) from the chunks k-1 .. k+1 of the previous solve,
+                # whose way back may still be running on the back stream
+                main.wait_event(self._phi_ready[min(k + 1, self.K - 1)])
             for s in self.slabs:
                 s.ck(s.L.ek_stream_collide_save_range(s.h, int(full), b0, b1, int(k == self.K - 1)),
                      "ek_stream_collide_save_range")
@@ -610,6 +648,10 @@ class SlabGroup:
                 self.poisson()
             else:
                 self.poisson_rest(pending)
+                if full or not self.overlap_back:
+                    self.join_back()
+                    self._mark("poisson_way_back")
+                # else: the way back of the last chunks runs behind the next step's first LBM launches
             with self._on_stream(self.halo_stream):
                 self.halo_exchange_finish(phase, hnd)
             main.wait_stream(self.halo_stream)

@@ -206,6 +206,10 @@ ek_status ek_halo_unpack(ek_handle *h, int phase, const double *from_left, const
 /* one ghost column of phi per face (NY x NZ doubles) for the fused E = -grad(phi) */
 ek_status ek_phi_halo_pack(ek_handle *h, double *to_left, double *to_right);
 ek_status ek_phi_halo_unpack(ek_handle *h, const double *from_left, const double *from_right);
+/* the same for the planes [z0, z1) only; the buffers keep the full [z][y] layout, so the
+ * planes of a range are the contiguous slice [z0*NY, z1*NY) */
+ek_status ek_phi_halo_pack_range(ek_handle *h, int z0, int z1, double *to_left, double *to_right);
+ek_status ek_phi_halo_unpack_range(ek_handle *h, int z0, int z1, const double *from_left, const double *from_right);
 /* distributed Poisson stage: c+ - c- array, the z-solve on a block of ky rows
  * of the full-x spectrum [NZ-2][kyl][NXglobal] complex, and the epilogue
  * (wall planes of phi, flags) once the host has written phi's interior */
