@@ -349,6 +349,7 @@ ek_status ek_init_fields(ek_handle *h)
     const EkConst &c = h->c;
     const size_t bytes = (size_t)c.N * sizeof(double);
     ek_launch_initialization(c, h->p, h->fld, h->stream);                       // LBM.cu:76
+    h->phi_walls_dirty = true;
     EK_CUDA(h, cudaMemcpyAsync(h->phi_old, h->fld[EK_PHI], bytes, cudaMemcpyDeviceToDevice, h->stream));  // LBM.cu:82-86
     for (int i = 0; i < h->p.pb_iters; ++i) {                                     // LBM.cu:89
         ek_launch_pbe(c, h->p, h->fld[EK_PHI], h->fld[EK_CHARGE], h->fld[EK_CHARGEN], h->dq, h->stream);
@@ -359,6 +360,7 @@ ek_status ek_init_fields(ek_handle *h)
                               h->fld[EK_EY], h->fld[EK_EZ], h->poisson_path, h->dc_mode, h->dc_ghat0, h->stream, &n);  // LBM.cu:96
         if (st != EK_OK) return st;
         ek_launch_pbe_relax(c, h->p.PB_omega, h->fld[EK_PHI], h->phi_old, h->stream);  // LBM.cu:98-104
+        h->phi_walls_dirty = true;   // the relaxation mixes the wall planes too: the next solve re-imposes them
     }
     EK_CUDA(h, cudaGetLastError());
     h->fields_ready = true;

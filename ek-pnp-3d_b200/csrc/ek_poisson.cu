@@ -25,7 +25,7 @@
 //    mu = kx^2 + ky^2 + (4/dz^2) sin^2(kz dz/2) (poisson.cu:174), persistent
 //    scratch instead of 3 cudaMalloc + 3 cudaFree per call (poisson.cu:77-102).
 //    Kept as the literal cross-check and for EK_DC_LITERAL.
-#include "ek_internal.cuh"
+#include "ek_handle.h"
 
 #include <math.h>
 #include <vector>
@@ -114,11 +114,19 @@ __global__ void k_zfactor(int ncols, int NXH, int M, const double *__restrict__ 
 //   d_j  = dz^2 * ( -(F/eps) * dq^_j  -  [j=0] V0/dz^2 * NXY  -  [j=M-1] V1/dz^2 * NXY )   (lift: (0,0) column only)
 //   d'_j = (d_j - d'_{j-1}) c'_j ;   phi^_j = d'_j - c'_j phi^_{j+1}
 // The result is scaled by 1/(NX*NY) for cuFFT's unnormalised inverse.
+// planes fetched ahead of the recurrence per thread: 16 measured best at 256^3 (Poisson stage
+// 0.354 ms against 0.383 with 8 and 0.390 with 32; 64-thread blocks make no difference)
+#ifndef EK_ZSOLVE_UNROLL
+#define EK_ZSOLVE_UNROLL 16
+#endif
+#ifndef EK_ZSOLVE_BLOCK
+#define EK_ZSOLVE_BLOCK 128
+#endif
 // Layout: x[blockIdx.y * x_outer + j * xj + r], cp[j * ncols + blockIdx.y * cp_outer + (r >> 1)]: blockIdx.y = 0
 // and xj = nreal for the single-GPU half spectrum [j][ky][kx]; blockIdx.y = local ky row and xj = 2*NXg for
 // the distributed solve's pencils [ky][j][kx] (ek_slab_poisson.cu).
 template <int UNROLL>
-__global__ void __launch_bounds__(128) k_zsolve(int nreal, int ncols, int M, double *__restrict__ x,
+__global__ void __launch_bounds__(EK_ZSOLVE_BLOCK) k_zsolve(int nreal, int ncols, int M, double *__restrict__ x,
                                                 const double *__restrict__ cp, double scale_dz2, double lift0,
                                                 double lift1, double norm, double dc_offset, int lift_r,
                                                 long long xj, long long x_outer, int cp_outer)
@@ -279,7 +287,7 @@ void ek_launch_zfactor_cols(int ncols, int NXg, int NY, int ky0, int M, double L
 void ek_launch_zsolve(int nreal, int ncols, int M, double *x, const double *cp, double scale_dz2, double lift0,
                       double lift1, double norm, double dc_offset, int lift_r, cudaStream_t st)
 {
-    k_zsolve<8><<<(nreal + 127) / 128, 128, 0, st>>>(nreal, ncols, M, x, cp, scale_dz2, lift0, lift1, norm, dc_offset,
+    k_zsolve<EK_ZSOLVE_UNROLL><<<(nreal + EK_ZSOLVE_BLOCK - 1) / EK_ZSOLVE_BLOCK, EK_ZSOLVE_BLOCK, 0, st>>>(nreal, ncols, M, x, cp, scale_dz2, lift0, lift1, norm, dc_offset,
                                                        lift_r, nreal, 0, 0);
 }
 
@@ -288,8 +296,8 @@ void ek_launch_zsolve_rows(int rows, int NXg, int M, double *x, const double *cp
                            double lift1, double norm, double dc_offset, bool has_dc, cudaStream_t st)
 {
     const int nreal = 2 * NXg;
-    dim3 grid((nreal + 127) / 128, rows);
-    k_zsolve<8><<<grid, 128, 0, st>>>(nreal, rows * NXg, M, x, cp, scale_dz2, lift0, lift1, norm, dc_offset,
+    dim3 grid((nreal + EK_ZSOLVE_BLOCK - 1) / EK_ZSOLVE_BLOCK, rows);
+    k_zsolve<EK_ZSOLVE_UNROLL><<<grid, EK_ZSOLVE_BLOCK, 0, st>>>(nreal, rows * NXg, M, x, cp, scale_dz2, lift0, lift1, norm, dc_offset,
                                         has_dc ? 0 : -1, (long long)nreal, (long long)M * nreal, NXg);
 }
 
@@ -353,12 +361,18 @@ ek_status ek_poisson_solve(ek_handle *h, EkPoisson &P, const ek_params &p, const
         const double nxy = (double)c.NX * (double)c.NY;
         const double size = (double)((unsigned int)c.NX * (unsigned int)c.NY * (unsigned int)P.NE);
         const double off = dc_mode == EK_DC_PRESCRIBED ? -dc_ghat0 / size : 0.0;
-        k_zsolve<8><<<(nreal + 127) / 128, 128, 0, st>>>(nreal, ncols, M, reinterpret_cast<double *>(P.spec2), P.cp,
+        k_zsolve<EK_ZSOLVE_UNROLL><<<(nreal + EK_ZSOLVE_BLOCK - 1) / EK_ZSOLVE_BLOCK, EK_ZSOLVE_BLOCK, 0, st>>>(nreal, ncols, M, reinterpret_cast<double *>(P.spec2), P.cp,
                                                            -(c.CtoC / c.eps) * c.dz * c.dz, -c.voltage * nxy,
                                                            -c.voltage2 * nxy, 1.0 / nxy, off, 0, nreal, 0, 0);
         EK_CUFFT(h, cufftExecZ2D(P.plan2_inv, P.spec2, phi + c.plane));
-        k_set_walls<<<dim3((c.NX + 127) / 128, c.NY), b, 0, st>>>(c, phi);
-        n = 2;
+        n = 1;
+        // the transforms never touch the wall planes: re-impose them only when something else wrote phi
+        // (start-up relaxation, uploads; poisson.cu:195-201 does it on every call)
+        if (h->phi_walls_dirty || h->fld_external[EK_PHI]) {   // an adopted array may be written by its owner
+            k_set_walls<<<dim3((c.NX + 127) / 128, c.NY), b, 0, st>>>(c, phi);
+            h->phi_walls_dirty = false;
+            n = 2;
+        }
     } else {
         ek_status s1 = create_path1(h, P, st);
         if (s1 != EK_OK) return s1;
@@ -369,6 +383,7 @@ ek_status ek_poisson_solve(ek_handle *h, EkPoisson &P, const ek_params &p, const
         EK_CUFFT(h, cufftExecZ2D(P.plan_inv, P.spec, P.real_ext));
         const double size = (double)((unsigned int)c.NX * (unsigned int)c.NY * (unsigned int)P.NE);  // LBM.h:38
         k_unpack<<<gz, b, 0, st>>>(c, P.real_ext, size, phi);
+        h->phi_walls_dirty = false;
         n = 3;
     }
     if (Ex) { ek_launch_efield(c, phi, Ex, Ey, Ez, st); ++n; }
