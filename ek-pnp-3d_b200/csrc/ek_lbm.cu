@@ -390,7 +390,9 @@ __global__ void __launch_bounds__(128, EK_MIN_CTAS) ek_step_kernel(const __grid_
     __shared__ Sh sh;
     const EkConst &c = a.c;
     const int lane = threadIdx.x & 31;
-    const int role = threadIdx.x >> 5;
+    // broadcast through a shuffle: tells the compiler that the role is warp-uniform, so that the role's
+    // loop counters, plane bases and branches can live in the uniform datapath
+    const int role = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     int x = blockIdx.x * 32 + lane;
     const bool act = x < c.NX;
     if (!act) x = c.NX - 1;  // clamped duplicate: loads stay in bounds, stores are masked
