@@ -301,12 +301,14 @@ __device__ __forceinline__ void fluid_node(const StepArgs &a, Sh &sh, const int 
     const double rho = sum27(S);
     double m[3];
     momentum(S, m);
+    // 1/rho does not depend on the other sets: its latency overlaps the momentum sums and the wait
+    // at the barrier instead of sitting between the two barriers where three warps wait for it
+    const double rhoinv = 1.0 / rho;
     bar_moments<NT>();
     const double E[3] = {sh.E[0][lane], sh.E[1][lane], sh.E[2][lane]};
     const double dq = sh.cp[lane] - sh.cn[lane];
     double F[3], ex_[3], u[3];
     node_force_and_momentum(c, m, dq, sh.T[lane], E, F, ex_);
-    const double rhoinv = 1.0 / rho;
     if (!LEAN && z == 0) {
         // u(z=0) = -(momentum expression of z=1) / rho(z=0)   (LBM.cu:778-800)
         u[0] = -rhoinv * expr1[0]; u[1] = -rhoinv * expr1[1]; u[2] = -rhoinv * expr1[2];
@@ -384,6 +386,8 @@ __device__ __forceinline__ void fluid_role(const StepArgs &a, Sh &sh, const int 
 #ifndef EK_MIN_CTAS
 #define EK_MIN_CTAS 4   // 128 registers; 3 (168 registers, no rematerialisation) measured slower, DESIGN.md 3.6
 #endif
+// (a variant without the store predicate for NX % 32 == 0 was measured: the odd kernel then spills 128 B
+// and the pass takes 5.01 instead of 4.92 ms at 256^3)
 template <int MODE, bool FULL, bool EARR, bool LEAN>
 __global__ void __launch_bounds__(128, EK_MIN_CTAS) ek_step_kernel(const __grid_constant__ StepArgs a)
 {
