@@ -57,6 +57,15 @@ __device__ __forceinline__ size_t dq_at(const EkConst &c, const Nbr &nb, int z)
 #elif defined(EK_CACHE_CG)
 #define EK_LD(p) __ldcg(p)
 #define EK_ST(p, v) __stcg((p), (v))
+#elif defined(EK_CACHE_LDCG)
+#define EK_LD(p) __ldcg(p)
+#define EK_ST(p, v) (*(p) = (v))
+#elif defined(EK_CACHE_STCG)
+#define EK_LD(p) (*(p))
+#define EK_ST(p, v) __stcg((p), (v))
+#elif defined(EK_CACHE_LDLU)
+#define EK_LD(p) __ldlu(p)
+#define EK_ST(p, v) (*(p) = (v))
 #else
 #define EK_LD(p) (*(p))
 #define EK_ST(p, v) (*(p) = (v))
