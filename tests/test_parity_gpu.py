@@ -551,3 +551,47 @@ def test_read_data_restores_the_reference_text_restart(ek, tmp_path):
         assert np.abs(got[k] - a).max() <= 5.1e-7, k
     with pytest.raises(ek.EkError):
         ek.Simulation(ek.default_params(NX=12, NY=4, NZ=11)).read_data(path)   # too few cells
+
+
+# ---------------------------------------------------------------------------
+# the reference's main() over the C ABI (examples/ek_main.cpp)
+# ---------------------------------------------------------------------------
+def test_cpp_main_matches_the_python_host(ek, tmp_path):
+    """examples/ek_main.cpp = main.cu:19-295 on the C ABI: same flow (stdin prompt, start-up,
+    loop with dumps and diagnostics, data_end.dat), compared with the same run driven from Python"""
+    import subprocess
+    exe = os.path.join(util.ROOT, "ek-pnp-3d_b200", "ek_main")
+    if not os.path.exists(exe):
+        pytest.skip("ek_main not built")
+    args = ["--nx", "12", "--ny", "4", "--nz", "9", "--nsteps", "24", "--nsave", "10", "--print-current", "5",
+            "--pb-iters", "30", "--checkpoint", "state.ekc"]
+    out = subprocess.run([exe] + args, input="0\n", capture_output=True, text=True, cwd=tmp_path, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert "Initializing..." in out.stdout and "speed:" in out.stdout and "Current =" in out.stdout
+    for f in ("data.dat", "umax.dat", "data_end.dat", "state.ekc"):
+        assert (tmp_path / f).stat().st_size > 0, f
+    assert open(tmp_path / "data.dat").read().count("ZONE T=") == 5          # t = 0, i = 1, 11, 21 (i % NSAVE == 1), end
+    over = dict(NX=12, NY=4, NZ=9, pb_iters=30)
+    sim = ek.Simulation(ek.default_params(**over))
+    sim.init()
+    sim.step(24)
+    want = sim.fields()
+    sim.close()
+    raw = np.loadtxt(tmp_path / "data_end.dat").reshape(9, 4, 12, 12)
+    cols = {"ux": 1, "uy": 2, "uz": 3, "rho": 4, "charge": 5, "chargen": 6, "phi": 7, "Ex": 8, "Ey": 9, "Ez": 10, "T": 11}
+    for k, j in cols.items():
+        a = want[k].copy()
+        if k in ("rho", "charge", "chargen", "ux", "uy", "uz"):     # dump-time wall extrapolation, LBM.cu:2598-2613
+            a[0] = 2.0 * a[1] - a[2]
+            a[-1] = 2.0 * a[-2] - a[-3]
+        assert np.abs(raw[..., j] - a).max() <= 5.1e-7, k
+    # the checkpoint written by the C++ host resumes in the Python host
+    sim = ek.Simulation(ek.default_params(**over))
+    sim.checkpoint_load(str(tmp_path / "state.ekc"))
+    for k in ("rho", "phi", "T"):
+        assert np.array_equal(sim.field(k), want[k]), k
+    sim.close()
+    # restart from the text file, as the reference's "press 1" branch
+    out = subprocess.run([exe, "--nx", "12", "--ny", "4", "--nz", "9", "--nsteps", "2"], input="1\n", capture_output=True,
+                         text=True, cwd=tmp_path, timeout=120)
+    assert out.returncode == 0 and "Reading previous data..." in out.stdout, out.stderr
