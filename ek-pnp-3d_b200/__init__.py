@@ -136,6 +136,19 @@ def load_library():
     L.ek_checkpoint_load.argtypes = [H, C.c_char_p, C.POINTER(C.c_double)]
     L.ek_set_populations.argtypes = [H, C.c_int, C.c_void_p]
     L.ek_populations_restored.argtypes = [H]
+    # native single-process multi-GPU driver (ek_multi.cu)
+    L.ek_multi_create.argtypes = [C.POINTER(Params), C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(H)]
+    for name in ("ek_multi_destroy", "ek_multi_init_fields", "ek_multi_init_equilibrium", "ek_multi_init",
+                 "ek_multi_sync", "ek_multi_slabs"):
+        getattr(L, name).argtypes = [H]
+    L.ek_multi_step.argtypes = [H, C.c_int]
+    L.ek_multi_step_timed.argtypes = [H, C.c_int, C.POINTER(C.c_float)]
+    L.ek_multi_get_field.argtypes = [H, C.c_int, C.c_void_p]
+    L.ek_multi_set_fields.argtypes = [H, C.POINTER(C.c_void_p)]
+    L.ek_multi_slab.argtypes = [H, C.c_int]
+    L.ek_multi_slab.restype = C.c_void_p
+    L.ek_multi_last_error.argtypes = [H]
+    L.ek_multi_last_error.restype = C.c_char_p
     _lib = L
     return L
 
@@ -348,3 +361,72 @@ class Simulation:
         self._ck(self.L.ek_checkpoint_load(self.h, path.encode(), C.byref(t)), "ek_checkpoint_load")
         self.t = t.value
         return t.value
+
+
+class MultiSimulation:
+    """The x-slab path driven natively from this one process (ek_multi.cu): one slab per entry of
+    `devices` (entries may repeat), peer access instead of NCCL.  Mirrors Simulation."""
+
+    def __init__(self, params: Params, devices, poisson_chunks: int = 0):
+        self.L = load_library()
+        self.p = params
+        self.h = C.c_void_p()
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        st = self.L.ek_multi_create(C.byref(self.p), len(devices), devs, int(poisson_chunks), C.byref(self.h))
+        if st != 0:
+            self.h = C.c_void_p()
+            raise EkError(f"ek_multi_create failed: {_STATUS.get(st, st)}")
+        self.shape = (self.p.NZ, self.p.NY, self.p.NX)
+
+    def _ck(self, st: int, what: str):
+        if st != 0:
+            msg = self.L.ek_multi_last_error(self.h)
+            raise EkError(f"{what}: {_STATUS.get(st, st)}: {msg.decode() if msg else ''}")
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.L.ek_multi_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def init(self):
+        self._ck(self.L.ek_multi_init(self.h), "ek_multi_init")
+
+    def initialization(self):
+        self._ck(self.L.ek_multi_init_fields(self.h), "ek_multi_init_fields")
+
+    def init_equilibrium(self):
+        self._ck(self.L.ek_multi_init_equilibrium(self.h), "ek_multi_init_equilibrium")
+
+    def step(self, nsteps: int = 1):
+        self._ck(self.L.ek_multi_step(self.h, int(nsteps)), "ek_multi_step")
+
+    def step_timed(self, nsteps: int) -> float:
+        ms = C.c_float()
+        self._ck(self.L.ek_multi_step_timed(self.h, int(nsteps), C.byref(ms)), "ek_multi_step_timed")
+        return ms.value
+
+    def set_fields(self, fields: dict):
+        arr = (C.c_void_p * len(FIELDS))()
+        keep = []
+        for i, n in enumerate(FIELDS):
+            if n in fields and fields[n] is not None:
+                a = np.ascontiguousarray(fields[n], dtype=np.float64)
+                keep.append(a)
+                arr[i] = a.ctypes.data
+            else:
+                arr[i] = None
+        self._ck(self.L.ek_multi_set_fields(self.h, arr), "ek_multi_set_fields")
+
+    def field(self, name: str) -> np.ndarray:
+        a = np.empty(self.shape, dtype=np.float64)
+        self._ck(self.L.ek_multi_get_field(self.h, FIELDS.index(name), a.ctypes.data), "ek_multi_get_field")
+        return a
+
+    def fields(self) -> dict:
+        return {n: self.field(n) for n in FIELDS}

@@ -261,6 +261,30 @@ ek_status ek_init_uniform(ek_handle *h);
 ek_status ek_pbe(ek_handle *h);
 ek_status ek_pbe_relax(ek_handle *h);
 
+/* ------------------------------------------------------------------------
+ * Multi-GPU from ONE host process (ek_multi.cu): the x-slab path driven natively,
+ * for a C++ caller such as the reference's main().  One slab per entry of
+ * `devices` (entries may repeat); halos and the Poisson transposes go through
+ * CUDA peer access inside the process, cross-device ordering through events.
+ * Same call sequence as the single-GPU handle; ek_multi_slab() gives access to
+ * the per-slab handles (options, counters).  Global arrays are in the
+ * reference's layout NX*(NY*z+y)+x over the WHOLE domain, in host memory.
+ * ------------------------------------------------------------------------ */
+typedef struct ek_multi ek_multi;
+ek_status ek_multi_create(const ek_params *global, int nslabs, const int *devices, int poisson_chunks, ek_multi **out);
+ek_status ek_multi_destroy(ek_multi *m);
+ek_status ek_multi_init_fields(ek_multi *m);        /* initialization(), LBM.cu:68-146 */
+ek_status ek_multi_init_equilibrium(ek_multi *m);   /* init_equilibrium(), LBM.cu:150-463 */
+ek_status ek_multi_init(ek_multi *m);
+ek_status ek_multi_step(ek_multi *m, int nsteps);   /* main.cu:189-200 */
+ek_status ek_multi_step_timed(ek_multi *m, int nsteps, float *ms);
+ek_status ek_multi_sync(ek_multi *m);
+ek_status ek_multi_get_field(ek_multi *m, int id, double *host_global);
+ek_status ek_multi_set_fields(ek_multi *m, const double *const host_global[EK_NFIELDS]);
+int ek_multi_slabs(ek_multi *m);
+ek_handle *ek_multi_slab(ek_multi *m, int s);
+const char *ek_multi_last_error(ek_multi *m);
+
 #ifdef __cplusplus
 }
 #endif

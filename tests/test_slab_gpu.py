@@ -144,3 +144,44 @@ def test_peer_memory_transport_is_bitwise_identical_to_the_all_to_all(ek, slab):
     for k in util.FIELDS:
         for other in res[1:]:
             assert np.array_equal(res[0][k], other[k]), k
+
+
+@pytest.mark.parametrize("P", [1, 2, 4])
+def test_native_multi_driver_matches_the_python_slab_driver(ek, slab, P):
+    """ek_multi.cu (one process, peer copies, event barriers) against slab.py (LocalComm) and the oracle:
+    same kernels in the same order, so the fields agree bit for bit"""
+    over = dict(NX=32 * P, NY=6, NZ=13, exf=1.0e6, voltage2=-3.0e-3)
+    init = synthetic_init(over)
+    grp = slab.SlabGroup(ek, ek.default_params(**over), slab.LocalComm(P))   # same (automatic) chunking as ek_multi
+    grp.set_fields(init)
+    grp.init_equilibrium()
+    grp.step(2)
+    grp.step(3)
+    want = grp.gather_fields()
+    grp.close()
+    m = ek.MultiSimulation(ek.default_params(**over), [0] * P)
+    assert m.L.ek_multi_slabs(m.h) == P and m.L.ek_multi_slab(m.h, P) is None
+    m.set_fields(init)
+    m.init_equilibrium()
+    m.step(2)
+    m.step(3)
+    got = m.fields()
+    m.close()
+    ref, _ = oracle_run(over, init, 5)
+    check(util.field_errors(got, ref))
+    for k in util.FIELDS:
+        assert np.array_equal(got[k], want[k]), k
+
+
+def test_native_multi_driver_startup(ek):
+    over = dict(NX=32, NY=4, NZ=11, pb_iters=40)
+    sim = ek.Simulation(ek.default_params(**over))
+    sim.init()
+    sim.step(2)
+    want = sim.fields()
+    sim.close()
+    m = ek.MultiSimulation(ek.default_params(**over), [0, 0])
+    m.init()
+    m.step(2)
+    check(util.field_errors(m.fields(), want))
+    m.close()
