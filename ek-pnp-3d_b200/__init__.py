@@ -73,6 +73,7 @@ def load_library():
     L = C.CDLL(LIB_PATH)
     H = C.c_void_p
     L.ek_abi_version.restype = C.c_int
+    L.ek_device_count.restype = C.c_int
     L.ek_default_params.argtypes = [C.POINTER(Params)]
     L.ek_default_params.restype = None
     L.ek_create.argtypes = [C.POINTER(Params), C.c_int, C.POINTER(H)]

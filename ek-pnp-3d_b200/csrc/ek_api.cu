@@ -189,6 +189,13 @@ extern "C" {
 
 int ek_abi_version(void) { return EK_B200_ABI_VERSION; }
 
+int ek_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
 void ek_default_params(ek_params *p)
 {
     // LBM.h:29-125 as shipped

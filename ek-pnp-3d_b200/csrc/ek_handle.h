@@ -65,3 +65,15 @@ void ek_compute_consts(const ek_params &p, EkConst &c, bool slab);
 int ek_auto_zchunk(const EkConst &c);
 ek_status ek_alloc_state(ek_handle *h);
 StepArgs ek_step_args(ek_handle *h);
+
+// dumps from host arrays of a whole domain (ek_io.cu; shared with the multi-GPU driver)
+struct EkHostFields {
+    std::vector<double> f[EK_NFIELDS];
+};
+struct EkDumpGrid {
+    int NX, NY, NZ;
+    double dx, dy, dz;
+};
+void ek_io_extrapolate_walls(EkHostFields &H, int NX, int NY, int NZ);
+bool ek_io_write_tecplot(const char *path, const EkDumpGrid &g, const EkHostFields &H, double time, int append, int first);
+bool ek_io_write_end(const char *path, const EkDumpGrid &g, const EkHostFields &H, double time);

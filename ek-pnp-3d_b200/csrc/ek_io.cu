@@ -54,11 +54,7 @@ __global__ void k_max_uz(EkConst c, const double *uz, double *partial)
     if (threadIdx.x == 0) partial[(size_t)z * c.NY + y] = sh[0];
 }
 
-struct HostFields {
-    std::vector<double> f[EK_NFIELDS];
-};
-
-ek_status fetch_all(ek_handle *h, HostFields &H)
+ek_status fetch_all(ek_handle *h, EkHostFields &H)
 {
     const size_t cells = (size_t)h->c.NX * h->c.NY * h->c.NZ;
     for (int k = 0; k < EK_NFIELDS; ++k) {
@@ -66,8 +62,23 @@ ek_status fetch_all(ek_handle *h, HostFields &H)
         ek_status st = ek_get_field(h, k, H.f[k].data(), 0);
         if (st != EK_OK) return st;
     }
-    // LBM.cu:2527-2542
-    const int NX = h->c.NX, NY = h->c.NY, NZ = h->c.NZ;
+    ek_io_extrapolate_walls(H, h->c.NX, h->c.NY, h->c.NZ);
+    return EK_OK;
+}
+
+EkDumpGrid grid_of(ek_handle *h)
+{
+    EkDumpGrid g;
+    g.NX = h->c.NX; g.NY = h->c.NY; g.NZ = h->c.NZ;
+    g.dx = h->p.dx; g.dy = h->p.dy; g.dz = h->p.dz;
+    return g;
+}
+
+}  // namespace
+
+// dump-time linear extrapolation of rho, c+, c-, u onto the wall planes (LBM.cu:2527-2542)
+void ek_io_extrapolate_walls(EkHostFields &H, int NX, int NY, int NZ)
+{
     auto idx = [&](int x, int y, int z) { return (size_t)NX * ((size_t)NY * z + y) + x; };
     const int ext[6] = {EK_RHO, EK_CHARGE, EK_CHARGEN, EK_UX, EK_UY, EK_UZ};
     for (int y = 0; y < NY; ++y)
@@ -77,10 +88,44 @@ ek_status fetch_all(ek_handle *h, HostFields &H)
                 a[idx(x, y, 0)] = 2.0 * a[idx(x, y, 1)] - a[idx(x, y, 2)];
                 a[idx(x, y, NZ - 1)] = 2.0 * a[idx(x, y, NZ - 2)] - a[idx(x, y, NZ - 3)];
             }
-    return EK_OK;
 }
 
-}  // namespace
+// save_data_tecplot (LBM.cu:2492-2565) from host arrays of the whole domain
+bool ek_io_write_tecplot(const char *path, const EkDumpGrid &g, const EkHostFields &H, double time, int append, int first)
+{
+    FILE *f = fopen(path, append ? "ab" : "wb");
+    if (!f) return false;
+    const int NX = g.NX, NY = g.NY, NZ = g.NZ;
+    if (first)
+        fprintf(f, "%s\n",
+                "VARIABLES=\"x\",\"y\",\"z\",\"u\",\"v\",\"w\",\"p\",\"charge\",\"neg charge\",\"phi\",\"Ex\",\"Ey\",\"Ez\",\"Temperature\"");
+    fprintf(f, "\n");
+    fprintf(f, "ZONE T=\"t=%g\", F=POINT, I = %d, J = %d, K = %d\n", time, NX, NY, NZ);
+    for (int z = 0; z < NZ; ++z)
+        for (int y = 0; y < NY; ++y)
+            for (int x = 0; x < NX; ++x) {
+                const size_t i = (size_t)NX * ((size_t)NY * z + y) + x;
+                fprintf(f, "%g %g %g %g %g %g %g %g %10.6f %10.6f %10.6f %10.6f %10.6f %10.6f\n", g.dx * x, g.dy * y,
+                        g.dz * z, H.f[EK_UX][i], H.f[EK_UY][i], H.f[EK_UZ][i], H.f[EK_RHO][i], H.f[EK_CHARGE][i],
+                        H.f[EK_CHARGEN][i], H.f[EK_PHI][i], H.f[EK_EX][i], H.f[EK_EY][i], H.f[EK_EZ][i], H.f[EK_T][i]);
+            }
+    fclose(f);
+    return true;
+}
+
+// save_data_end (LBM.cu:2567-2627)
+bool ek_io_write_end(const char *path, const EkDumpGrid &g, const EkHostFields &H, double time)
+{
+    FILE *f = fopen(path, "wb");
+    if (!f) return false;
+    const size_t cells = (size_t)g.NX * g.NY * g.NZ;
+    for (size_t i = 0; i < cells; ++i)
+        fprintf(f, "%10.6f %10.6f %10.6f %10.6f %10.6f %10.6f %10.6f %10.6f %10.6f %10.6f %10.6f %10.6f\n", time,
+                H.f[EK_UX][i], H.f[EK_UY][i], H.f[EK_UZ][i], H.f[EK_RHO][i], H.f[EK_CHARGE][i], H.f[EK_CHARGEN][i],
+                H.f[EK_PHI][i], H.f[EK_EX][i], H.f[EK_EY][i], H.f[EK_EZ][i], H.f[EK_T][i]);
+    fclose(f);
+    return true;
+}
 
 extern "C" {
 
@@ -130,44 +175,26 @@ ek_status ek_max_uz(ek_handle *h, double *umax)
 ek_status ek_save_data_tecplot(ek_handle *h, const char *path, double time, int append, int first)
 {
     if (!h || !path) return EK_ERR_INVALID;
-    HostFields H;
+    EkHostFields H;
     ek_status st = fetch_all(h, H);
     if (st != EK_OK) return st;
-    FILE *f = fopen(path, append ? "ab" : "wb");
-    if (!f) { ek_set_error(h, std::string("cannot open ") + path); return EK_ERR_INVALID; }
-    const int NX = h->c.NX, NY = h->c.NY, NZ = h->c.NZ;
-    if (first)
-        fprintf(f, "%s\n",
-                "VARIABLES=\"x\",\"y\",\"z\",\"u\",\"v\",\"w\",\"p\",\"charge\",\"neg charge\",\"phi\",\"Ex\",\"Ey\",\"Ez\",\"Temperature\"");
-    fprintf(f, "\n");
-    fprintf(f, "ZONE T=\"t=%g\", F=POINT, I = %d, J = %d, K = %d\n", time, NX, NY, NZ);
-    for (int z = 0; z < NZ; ++z)
-        for (int y = 0; y < NY; ++y)
-            for (int x = 0; x < NX; ++x) {
-                const size_t i = (size_t)NX * ((size_t)NY * z + y) + x;
-                fprintf(f, "%g %g %g %g %g %g %g %g %10.6f %10.6f %10.6f %10.6f %10.6f %10.6f\n", h->p.dx * x,
-                        h->p.dy * y, h->p.dz * z, H.f[EK_UX][i], H.f[EK_UY][i], H.f[EK_UZ][i], H.f[EK_RHO][i],
-                        H.f[EK_CHARGE][i], H.f[EK_CHARGEN][i], H.f[EK_PHI][i], H.f[EK_EX][i], H.f[EK_EY][i],
-                        H.f[EK_EZ][i], H.f[EK_T][i]);
-            }
-    fclose(f);
+    if (!ek_io_write_tecplot(path, grid_of(h), H, time, append, first)) {
+        ek_set_error(h, std::string("cannot open ") + path);
+        return EK_ERR_INVALID;
+    }
     return EK_OK;
 }
 
 ek_status ek_save_data_end(ek_handle *h, const char *path, double time)
 {
     if (!h || !path) return EK_ERR_INVALID;
-    HostFields H;
+    EkHostFields H;
     ek_status st = fetch_all(h, H);
     if (st != EK_OK) return st;
-    FILE *f = fopen(path, "wb");
-    if (!f) { ek_set_error(h, std::string("cannot open ") + path); return EK_ERR_INVALID; }
-    const size_t cells = (size_t)h->c.NX * h->c.NY * h->c.NZ;
-    for (size_t i = 0; i < cells; ++i)
-        fprintf(f, "%10.6f %10.6f %10.6f %10.6f %10.6f %10.6f %10.6f %10.6f %10.6f %10.6f %10.6f %10.6f\n", time,
-                H.f[EK_UX][i], H.f[EK_UY][i], H.f[EK_UZ][i], H.f[EK_RHO][i], H.f[EK_CHARGE][i], H.f[EK_CHARGEN][i],
-                H.f[EK_PHI][i], H.f[EK_EX][i], H.f[EK_EY][i], H.f[EK_EZ][i], H.f[EK_T][i]);
-    fclose(f);
+    if (!ek_io_write_end(path, grid_of(h), H, time)) {
+        ek_set_error(h, std::string("cannot open ") + path);
+        return EK_ERR_INVALID;
+    }
     return EK_OK;
 }
 
@@ -181,7 +208,7 @@ ek_status ek_read_data(ek_handle *h, const char *path, double *time)
     FILE *f = fopen(path, "r");
     if (!f) { ek_set_error(h, std::string("cannot open ") + path); return EK_ERR_INVALID; }
     const size_t cells = (size_t)h->c.NX * h->c.NY * h->c.NZ;
-    HostFields H;
+    EkHostFields H;
     for (int k = 0; k < EK_NFIELDS; ++k) H.f[k].resize(cells);
     double t = 0.0;
     for (size_t i = 0; i < cells; ++i) {
@@ -256,7 +283,7 @@ ek_status ek_checkpoint_load(ek_handle *h, const char *path, double *time)
         return EK_ERR_INVALID;
     }
     const size_t cells = (size_t)h->c.NX * h->c.NY * h->c.NZ;
-    HostFields H;
+    EkHostFields H;
     bool ok = true;
     for (int k = 0; k < EK_NFIELDS && ok; ++k) {
         H.f[k].resize(cells);

@@ -322,4 +322,65 @@ ek_status ek_multi_set_fields(ek_multi *m, const double *const host_global[EK_NF
     return EK_OK;
 }
 
+// ---- diagnostics and dumps of the whole domain (LBM.cu:2492-2753) ----------------------------
+ek_status ek_multi_wall_current(ek_multi *m, double *current)
+{
+    if (!m || !current) return EK_ERR_INVALID;
+    double I = 0.0;
+    for (int s = 0; s < m->P; ++s) {
+        double Is = 0.0;
+        MK(m, m->h[s], ek_wall_current(m->h[s], &Is));
+        I += Is;
+    }
+    *current = I;
+    return EK_OK;
+}
+
+ek_status ek_multi_max_uz(ek_multi *m, double *umax)
+{
+    if (!m || !umax) return EK_ERR_INVALID;
+    double v = 0.0;
+    for (int s = 0; s < m->P; ++s) {
+        double vs = 0.0;
+        MK(m, m->h[s], ek_max_uz(m->h[s], &vs));
+        v = vs > v ? vs : v;
+    }
+    *umax = v;
+    return EK_OK;
+}
+
+static ek_status gather_all(ek_multi *m, EkHostFields &H)
+{
+    const size_t cells = (size_t)m->global.NX * m->global.NY * m->global.NZ;
+    for (int k = 0; k < EK_NFIELDS; ++k) {
+        H.f[k].resize(cells);
+        ek_status st = ek_multi_get_field(m, k, H.f[k].data());
+        if (st != EK_OK) return st;
+    }
+    ek_io_extrapolate_walls(H, m->global.NX, m->global.NY, m->global.NZ);
+    return EK_OK;
+}
+
+ek_status ek_multi_save_data_tecplot(ek_multi *m, const char *path, double time, int append, int first)
+{
+    if (!m || !path) return EK_ERR_INVALID;
+    EkHostFields H;
+    ek_status st = gather_all(m, H);
+    if (st != EK_OK) return st;
+    const EkDumpGrid g = {m->global.NX, m->global.NY, m->global.NZ, m->global.dx, m->global.dy, m->global.dz};
+    if (!ek_io_write_tecplot(path, g, H, time, append, first)) { m->err = std::string("cannot open ") + path; return EK_ERR_INVALID; }
+    return EK_OK;
+}
+
+ek_status ek_multi_save_data_end(ek_multi *m, const char *path, double time)
+{
+    if (!m || !path) return EK_ERR_INVALID;
+    EkHostFields H;
+    ek_status st = gather_all(m, H);
+    if (st != EK_OK) return st;
+    const EkDumpGrid g = {m->global.NX, m->global.NY, m->global.NZ, m->global.dx, m->global.dy, m->global.dz};
+    if (!ek_io_write_end(path, g, H, time)) { m->err = std::string("cannot open ") + path; return EK_ERR_INVALID; }
+    return EK_OK;
+}
+
 }  // extern "C"

@@ -9,8 +9,9 @@
 // overrides the ones that LBM.h makes people edit (grid, step counts, a few physical inputs):
 //     ek_main [--nx N] [--ny N] [--nz N] [--nsteps N] [--nsave N] [--print-current N]
 //             [--ext V/m] [--exf N/m3] [--uw m/s] [--th K] [--cinf mol] [--pb-iters N]
-//             [--restart 0|1] [--checkpoint file] [--resume file] [--device d]
-// Without --restart the program asks on stdin like main.cu:158-159.
+//             [--restart 0|1] [--checkpoint file] [--resume file] [--device d] [--gpus N]
+// Without --restart the program asks on stdin like main.cu:158-159.  --gpus N splits the domain into
+// N x-slabs on devices 0..N-1 of this process (ek_multi_*, NX must be divisible by 2N; new runs only).
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -19,20 +20,40 @@
 
 #include "ek_b200.h"
 
+static ek_multi *g_multi = nullptr;
+
 static void die(ek_handle *h, const char *what, ek_status st)
 {
     // the reference's contract: message on stderr, exit(-1) (LBM.cu:35-53)
-    fprintf(stderr, "%s failed: status %d: %s\n", what, (int)st, h ? ek_last_error(h) : "");
+    fprintf(stderr, "%s failed: status %d: %s\n", what, (int)st,
+            g_multi ? ek_multi_last_error(g_multi) : (h ? ek_last_error(h) : ""));
     exit(-1);
 }
 #define CK(call) do { ek_status _s = (call); if (_s != EK_OK) die(h, #call, _s); } while (0)
+
+// the same calls on one handle or on the slabs of an ek_multi
+struct Sim {
+    ek_handle *h = nullptr;
+    ek_multi *m = nullptr;
+    ek_status init_fields() { return m ? ek_multi_init_fields(m) : ek_init_fields(h); }
+    ek_status init_equilibrium() { return m ? ek_multi_init_equilibrium(m) : ek_init_equilibrium(h); }
+    ek_status step_timed(int n, float *ms) { return m ? ek_multi_step_timed(m, n, ms) : ek_step_timed(h, n, ms); }
+    ek_status tecplot(const char *p, double t, int append, int first)
+    {
+        return m ? ek_multi_save_data_tecplot(m, p, t, append, first) : ek_save_data_tecplot(h, p, t, append, first);
+    }
+    ek_status save_end(const char *p, double t) { return m ? ek_multi_save_data_end(m, p, t) : ek_save_data_end(h, p, t); }
+    ek_status wall_current(double *I) { return m ? ek_multi_wall_current(m, I) : ek_wall_current(h, I); }
+    ek_status max_uz(double *u) { return m ? ek_multi_max_uz(m, u) : ek_max_uz(h, u); }
+    ek_status sync() { return m ? ek_multi_sync(m) : ek_sync(h); }
+};
 
 int main(int argc, char **argv)
 {
     ek_params P;
     ek_default_params(&P);                                   // LBM.h:29-125 as shipped
     unsigned NSTEPS = 1000, NSAVE = 0, printCurrent = 50;     // LBM.h:122-125
-    int restart = -1, device = 0;
+    int restart = -1, device = 0, gpus = 1;
     const char *ckpt_out = nullptr, *ckpt_in = nullptr;
     bool grid_changed = false;
     for (int i = 1; i + 1 < argc; i += 2) {
@@ -53,6 +74,7 @@ int main(int argc, char **argv)
         else if (!strcmp(k, "--checkpoint")) ckpt_out = v;
         else if (!strcmp(k, "--resume")) ckpt_in = v;
         else if (!strcmp(k, "--device")) device = atoi(v);
+        else if (!strcmp(k, "--gpus")) gpus = atoi(v);
         else { fprintf(stderr, "unknown option %s\n", k); return 2; }
     }
     if (grid_changed) {   // LBM.h:40-42: the box follows the grid at the shipped spacing
@@ -62,8 +84,22 @@ int main(int argc, char **argv)
     if (printCurrent == 0) printCurrent = 1;
 
     ek_handle *h = nullptr;
-    ek_status st = ek_create(&P, device, &h);
-    if (st != EK_OK) die(nullptr, "ek_create (a CUDA device is required, there is no CPU path)", st);
+    Sim sim;
+    if (gpus > 1) {
+        if (ckpt_in || ckpt_out || restart == 1) { fprintf(stderr, "--gpus: restart files are single-GPU for now\n"); return 2; }
+        int devs[16];
+        const int ndev = ek_device_count() > 0 ? ek_device_count() : 1;
+        if (gpus > 16) gpus = 16;
+        for (int d = 0; d < gpus; ++d) devs[d] = d % ndev;   // fewer devices than slabs: slabs share devices
+        ek_status st = ek_multi_create(&P, gpus, devs, 0, &sim.m);
+        if (st != EK_OK) die(nullptr, "ek_multi_create (NX divisible by 2*gpus, <= 16 CUDA devices of one node)", st);
+        g_multi = sim.m;
+        restart = 0;
+    } else {
+        ek_status st = ek_create(&P, device, &h);
+        if (st != EK_OK) die(nullptr, "ek_create (a CUDA device is required, there is no CPU path)", st);
+        sim.h = h;
+    }
 
     printf("Simulating 3D electrokinetic flow (EK-PNP) on a %d x %d x %d grid\n", P.NX, P.NY, P.NZ);
     double t = 0.0;
@@ -80,12 +116,12 @@ int main(int argc, char **argv)
             CK(ek_read_data(h, "data_end.dat", &t));
         } else {
             printf("Initializing...\n");                                                    // main.cu:166
-            CK(ek_init_fields(h));                                                          // main.cu:169
+            CK(sim.init_fields());                                                          // main.cu:169
             t = 0;
         }
-        CK(ek_init_equilibrium(h));                                                         // main.cu:174
+        CK(sim.init_equilibrium());                                                         // main.cu:174
     }
-    CK(ek_save_data_tecplot(h, "data.dat", t, 0, 1));                                       // main.cu:178-179
+    CK(sim.tecplot("data.dat", t, 0, 1));                                                   // main.cu:178-179
     FILE *fumax = fopen("umax.dat", "wb+");                                                // main.cu:180
     if (!fumax) { fprintf(stderr, "cannot open umax.dat\n"); return 1; }
 
@@ -100,24 +136,24 @@ int main(int argc, char **argv)
             if (j % NSAVE == 1 || j % printCurrent == 1) { next = j; break; }
         const int n = (int)(next - i + 1);
         float ms = 0.0f;
-        CK(ek_step_timed(h, n, &ms));
+        CK(sim.step_timed(n, &ms));
         gpu_ms += ms;
         t += n * P.dt;
         i = next;
         if (i % NSAVE == 1) {
-            CK(ek_save_data_tecplot(h, "data.dat", t, 1, 1));                               // main.cu:206-209
+            CK(sim.tecplot("data.dat", t, 1, 1));                                           // main.cu:206-209
             printf("Iteration: %u, physical time: %g.\n", i, t);
         }
         if (i % printCurrent == 1) {
             double I = 0.0, umax = 0.0;
-            CK(ek_wall_current(h, &I));                                                     // main.cu:211-216
+            CK(sim.wall_current(&I));                                                       // main.cu:211-216
             printf("Iteration: %u, physical time: %g, Current = %g\n", i, t, I);
-            CK(ek_max_uz(h, &umax));                                                        // main.cu:221
+            CK(sim.max_uz(&umax));                                                          // main.cu:221
             fprintf(fumax, "%10.6f %10.6f\n", t, umax);                                     // LBM.cu:2747
         }
         ++i;
     }
-    CK(ek_sync(h));
+    CK(sim.sync());
     const double runtime = std::chrono::duration<double>(std::chrono::steady_clock::now() - begin).count();
     const double nodes_updated = (double)NSTEPS * (double)P.NX * P.NY * P.NZ;              // main.cu:239
     printf(" ----- performance information -----\n");                                       // main.cu:247-251
@@ -126,10 +162,10 @@ int main(int argc, char **argv)
     printf("             gpu runtime: %.3f (s)\n", 0.001 * gpu_ms);
     printf("                   speed: %.2f (Mlups)\n", nodes_updated / (1e6 * runtime));
 
-    CK(ek_save_data_tecplot(h, "data.dat", t, 1, 1));                                       // main.cu:253
+    CK(sim.tecplot("data.dat", t, 1, 1));                                                   // main.cu:253
     fclose(fumax);
-    CK(ek_save_data_end(h, "data_end.dat", t));                                             // main.cu:256-257
+    CK(sim.save_end("data_end.dat", t));                                                    // main.cu:256-257
     if (ckpt_out) CK(ek_checkpoint_save(h, ckpt_out, t));
-    ek_destroy(h);
+    if (sim.m) ek_multi_destroy(sim.m); else ek_destroy(h);
     return 0;
 }

@@ -160,6 +160,7 @@ ek_status ek_reset_counters(ek_handle *h);
 void *ek_stream(ek_handle *h);
 const char *ek_last_error(ek_handle *h);
 int ek_abi_version(void);
+int ek_device_count(void);   /* CUDA devices visible to the process (0: none -- there is no CPU path) */
 
 /* Diagnostics on device.  Replace current() (LBM.cu:2674-2710) and the
  * reduction of record_umax() (LBM.cu:2712-2753). */
@@ -281,6 +282,10 @@ ek_status ek_multi_step_timed(ek_multi *m, int nsteps, float *ms);
 ek_status ek_multi_sync(ek_multi *m);
 ek_status ek_multi_get_field(ek_multi *m, int id, double *host_global);
 ek_status ek_multi_set_fields(ek_multi *m, const double *const host_global[EK_NFIELDS]);
+ek_status ek_multi_wall_current(ek_multi *m, double *current);
+ek_status ek_multi_max_uz(ek_multi *m, double *umax);
+ek_status ek_multi_save_data_tecplot(ek_multi *m, const char *path, double time, int append, int first);
+ek_status ek_multi_save_data_end(ek_multi *m, const char *path, double time);
 int ek_multi_slabs(ek_multi *m);
 ek_handle *ek_multi_slab(ek_multi *m, int s);
 const char *ek_multi_last_error(ek_multi *m);

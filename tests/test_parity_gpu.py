@@ -591,6 +591,13 @@ def test_cpp_main_matches_the_python_host(ek, tmp_path):
     for k in ("rho", "phi", "T"):
         assert np.array_equal(sim.field(k), want[k]), k
     sim.close()
+    # the same run split into two x-slabs by the native multi-GPU driver (devices wrap on a 1-GPU box)
+    (tmp_path / "two").mkdir()
+    out2 = subprocess.run([exe] + args[:-2] + ["--gpus", "2"], capture_output=True, text=True, cwd=tmp_path / "two", timeout=120)
+    assert out2.returncode == 0, out2.stderr
+    raw2 = np.loadtxt(tmp_path / "two" / "data_end.dat").reshape(9, 4, 12, 12)
+    assert np.abs(raw2 - raw).max() <= 1.1e-6        # one unit of the six-decimal text format
+    assert open(tmp_path / "two" / "umax.dat").read().count("\n") == open(tmp_path / "umax.dat").read().count("\n")
     # restart from the text file, as the reference's "press 1" branch
     out = subprocess.run([exe, "--nx", "12", "--ny", "4", "--nz", "9", "--nsteps", "2"], input="1\n", capture_output=True,
                          text=True, cwd=tmp_path, timeout=120)
