@@ -143,6 +143,7 @@ def load_library():
                  "ek_multi_sync", "ek_multi_slabs"):
         getattr(L, name).argtypes = [H]
     L.ek_multi_step.argtypes = [H, C.c_int]
+    L.ek_multi_set_pipeline.argtypes = [H, C.c_int]
     L.ek_multi_step_timed.argtypes = [H, C.c_int, C.POINTER(C.c_float)]
     L.ek_multi_get_field.argtypes = [H, C.c_int, C.c_void_p]
     L.ek_multi_set_fields.argtypes = [H, C.POINTER(C.c_void_p)]

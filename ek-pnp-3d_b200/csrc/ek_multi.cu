@@ -24,6 +24,9 @@ struct ek_multi {
     std::vector<ek_handle *> h;
     std::vector<int> dev;
     std::vector<cudaEvent_t> ev;          // one per slab, re-recorded at every barrier
+    std::vector<cudaEvent_t> ev2;         // second set (side / halo streams)
+    std::vector<cudaStream_t> side, halo; // per slab: Poisson forward half behind the LBM launches; halos
+    bool pipeline = true;
     // halo buffers on each slab's device
     std::vector<double *> to_l, to_r, from_l, from_r;       // populations: ek_halo_doubles() each
     std::vector<double *> pto_l, pto_r, pfrom_l, pfrom_r;   // phi: NY*NZ each
@@ -54,6 +57,26 @@ ek_status fail(ek_multi *m, ek_handle *h, const char *what, ek_status st)
             return EK_ERR_CUDA;                                                    \
         }                                                                          \
     } while (0)
+
+// RAII: the calls of the C ABI made in this scope run on another stream of the slab's device
+struct OnStream {
+    ek_handle *h;
+    cudaStream_t saved;
+    OnStream(ek_handle *hh, cudaStream_t st) : h(hh), saved(hh->stream) { h->stream = st; }
+    ~OnStream() { h->stream = saved; }
+};
+
+// stream `a` waits for everything issued so far on stream `b` (same or another device)
+ek_status wait_for(ek_multi *m, int dev_a, cudaStream_t a, int dev_b, cudaStream_t b, cudaEvent_t ev)
+{
+    {
+        DeviceGuard g(dev_b);
+        MCUDA(m, cudaEventRecord(ev, b));
+    }
+    DeviceGuard g(dev_a);
+    MCUDA(m, cudaStreamWaitEvent(a, ev, 0));
+    return EK_OK;
+}
 
 // every slab's stream waits until every slab's stream has reached this point
 ek_status barrier_all(ek_multi *m)
@@ -87,6 +110,39 @@ ek_status ring_exchange(ek_multi *m, std::vector<double *> &to_l, std::vector<do
     return EK_OK;
 }
 
+// population halos on the halo streams, next to whatever the main streams do meanwhile
+ek_status halo_exchange_async(ek_multi *m, int phase)
+{
+    const size_t n = (size_t)ek_halo_doubles(m->h[0]);
+    for (int s = 0; s < m->P; ++s) {   // after this slab's LBM pass
+        MK(m, nullptr, wait_for(m, m->dev[s], m->halo[s], m->dev[s], m->h[s]->stream, m->ev2[s]));
+        OnStream on(m->h[s], m->halo[s]);
+        MK(m, m->h[s], ek_halo_pack(m->h[s], phase, m->to_l[s], m->to_r[s]));
+    }
+    for (int s = 0; s < m->P; ++s) {
+        DeviceGuard g(m->dev[s]);
+        MCUDA(m, cudaEventRecord(m->ev2[s], m->halo[s]));
+    }
+    for (int s = 0; s < m->P; ++s) {
+        const int l = (s + m->P - 1) % m->P, r = (s + 1) % m->P;
+        DeviceGuard g(m->dev[s]);
+        MCUDA(m, cudaStreamWaitEvent(m->halo[s], m->ev2[l], 0));
+        MCUDA(m, cudaStreamWaitEvent(m->halo[s], m->ev2[r], 0));
+        MCUDA(m, cudaMemcpyAsync(m->from_l[s], m->to_r[l], n * sizeof(double), cudaMemcpyDefault, m->halo[s]));
+        MCUDA(m, cudaMemcpyAsync(m->from_r[s], m->to_l[r], n * sizeof(double), cudaMemcpyDefault, m->halo[s]));
+        OnStream on(m->h[s], m->halo[s]);
+        MK(m, m->h[s], ek_halo_unpack(m->h[s], phase, m->from_l[s], m->from_r[s]));
+    }
+    return EK_OK;
+}
+
+ek_status halo_join(ek_multi *m)
+{
+    for (int s = 0; s < m->P; ++s)
+        MK(m, nullptr, wait_for(m, m->dev[s], m->h[s]->stream, m->dev[s], m->halo[s], m->ev2[s]));
+    return EK_OK;
+}
+
 ek_status halo_exchange(ek_multi *m, int phase)
 {
     for (int s = 0; s < m->P; ++s) MK(m, m->h[s], ek_halo_pack(m->h[s], phase, m->to_l[s], m->to_r[s]));
@@ -105,6 +161,8 @@ ek_status phi_halo_exchange(ek_multi *m)
     return EK_OK;
 }
 
+ek_status poisson_rest(ek_multi *m, bool join_halo);
+
 // the distributed fast_Poisson(): c+ - c- -> phi, ghost columns included
 ek_status poisson(ek_multi *m)
 {
@@ -113,6 +171,33 @@ ek_status poisson(ek_multi *m)
             MK(m, m->h[s], ek_slab_poisson_forward(m->h[s], k));
             MK(m, m->h[s], ek_slab_poisson_push_x(m->h[s], k));
         }
+    return poisson_rest(m, false);
+}
+
+// One LBM pass launched chunk by chunk; chunk k's y-transform and its pushes into the peers' pencils
+// run on the side streams behind the launches of the later chunks (as slab.py's lbm_and_forward)
+ek_status lbm_and_forward(ek_multi *m, int full)
+{
+    for (int k = 0; k < m->K; ++k) {
+        for (int s = 0; s < m->P; ++s) {
+            const EkSlabPoisson &S = m->h[s]->sp;
+            MK(m, m->h[s], ek_stream_collide_save_range(m->h[s], full, S.block0[k], S.block0[k + 1], k == m->K - 1));
+        }
+        for (int s = 0; s < m->P; ++s) {
+            MK(m, nullptr, wait_for(m, m->dev[s], m->side[s], m->dev[s], m->h[s]->stream, m->ev[s]));
+            OnStream on(m->h[s], m->side[s]);
+            MK(m, m->h[s], ek_slab_poisson_forward(m->h[s], k));
+            MK(m, m->h[s], ek_slab_poisson_push_x(m->h[s], k));
+        }
+    }
+    return EK_OK;
+}
+
+ek_status poisson_rest(ek_multi *m, bool join_halo)
+{
+    if (m->pipeline)   // the main streams join their side streams before the barrier
+        for (int s = 0; s < m->P; ++s)
+            MK(m, nullptr, wait_for(m, m->dev[s], m->h[s]->stream, m->dev[s], m->side[s], m->ev[s]));
     MK(m, nullptr, barrier_all(m));   // every slab's rows have landed in everybody's pencils
     for (int s = 0; s < m->P; ++s) MK(m, m->h[s], ek_slab_poisson_solve(m->h[s]));
     for (int k = 0; k < m->K; ++k)
@@ -121,6 +206,9 @@ ek_status poisson(ek_multi *m)
     for (int k = 0; k < m->K; ++k)
         for (int s = 0; s < m->P; ++s) MK(m, m->h[s], ek_slab_poisson_backward(m->h[s], k));
     for (int s = 0; s < m->P; ++s) MK(m, m->h[s], ek_poisson_finish(m->h[s], 0));
+    // the population halos have had the whole stage to travel: the main streams join them here, so that
+    // the barrier of the phi exchange also orders every neighbour's copy before anybody's next pack
+    if (join_halo) MK(m, nullptr, halo_join(m));
     return phi_halo_exchange(m);
 }
 
@@ -129,6 +217,9 @@ void release(ek_multi *m)
     for (int s = 0; s < (int)m->h.size(); ++s) {
         DeviceGuard g(m->dev[s]);
         if (s < (int)m->ev.size() && m->ev[s]) cudaEventDestroy(m->ev[s]);
+        if (s < (int)m->ev2.size() && m->ev2[s]) cudaEventDestroy(m->ev2[s]);
+        if (s < (int)m->side.size() && m->side[s]) cudaStreamDestroy(m->side[s]);
+        if (s < (int)m->halo.size() && m->halo[s]) cudaStreamDestroy(m->halo[s]);
         auto fr = [&](std::vector<double *> &v) { if (s < (int)v.size()) cudaFree(v[s]); };
         fr(m->to_l); fr(m->to_r); fr(m->from_l); fr(m->from_r);
         fr(m->pto_l); fr(m->pto_r); fr(m->pfrom_l); fr(m->pfrom_r);
@@ -175,6 +266,14 @@ ek_status ek_multi_create(const ek_params *global, int nslabs, const int *device
         cudaEvent_t e = nullptr;
         if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { st = EK_ERR_CUDA; break; }
         m->ev.push_back(e);
+        cudaEvent_t e2 = nullptr;
+        cudaStream_t s1 = nullptr, s2 = nullptr;
+        if (cudaEventCreateWithFlags(&e2, cudaEventDisableTiming) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking) != cudaSuccess) { st = EK_ERR_CUDA; break; }
+        m->ev2.push_back(e2);
+        m->side.push_back(s1);
+        m->halo.push_back(s2);
         st = ek_slab_poisson_setup(m->h[s], poisson_chunks > 0 ? poisson_chunks : 4);
         if (st != EK_OK) break;
         const size_t nh = (size_t)ek_halo_doubles(m->h[s]) * sizeof(double);
@@ -205,6 +304,15 @@ ek_status ek_multi_destroy(ek_multi *m)
     if (!m) return EK_ERR_INVALID;
     for (int s = 0; s < m->P; ++s) ek_sync(m->h[s]);
     release(m);
+    return EK_OK;
+}
+
+// 1 (default): forward half of the Poisson stage behind the LBM launches, halos next to the Poisson
+// stage; 0: everything in sequence on one stream per slab
+ek_status ek_multi_set_pipeline(ek_multi *m, int on)
+{
+    if (!m) return EK_ERR_INVALID;
+    m->pipeline = on != 0;
     return EK_OK;
 }
 
@@ -257,9 +365,15 @@ ek_status ek_multi_step(ek_multi *m, int nsteps)
     for (int i = 0; i < nsteps; ++i) {
         const int full = (i == nsteps - 1);
         const int phase = ek_lbm_parity(m->h[0]) == 0 ? 0 : 1;
-        for (int s = 0; s < m->P; ++s) MK(m, m->h[s], ek_stream_collide_save(m->h[s], full));
-        MK(m, nullptr, halo_exchange(m, phase));
-        MK(m, nullptr, poisson(m));
+        if (m->pipeline && m->K > 1) {
+            MK(m, nullptr, lbm_and_forward(m, full));
+            MK(m, nullptr, halo_exchange_async(m, phase));   // next to the Poisson stage
+            MK(m, nullptr, poisson_rest(m, true));
+        } else {
+            for (int s = 0; s < m->P; ++s) MK(m, m->h[s], ek_stream_collide_save(m->h[s], full));
+            MK(m, nullptr, halo_exchange(m, phase));
+            MK(m, nullptr, poisson(m));
+        }
         if (full)
             for (int s = 0; s < m->P; ++s) MK(m, m->h[s], ek_compute_efield(m->h[s]));
     }

@@ -171,6 +171,17 @@ def test_native_multi_driver_matches_the_python_slab_driver(ek, slab, P):
     check(util.field_errors(got, ref))
     for k in util.FIELDS:
         assert np.array_equal(got[k], want[k]), k
+    # without the stream pipeline: same numbers
+    m = ek.MultiSimulation(ek.default_params(**over), [0] * P)
+    assert m.L.ek_multi_set_pipeline(m.h, 0) == 0
+    m.set_fields(init)
+    m.init_equilibrium()
+    m.step(2)
+    m.step(3)
+    plain = m.fields()
+    m.close()
+    for k in util.FIELDS:
+        assert np.array_equal(plain[k], want[k]), k
 
 
 def test_native_multi_driver_startup(ek):

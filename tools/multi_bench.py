@@ -34,12 +34,14 @@ def main():
     p = ek.default_params(NX=1024 * n, NY=512, NZ=256, pb_iters=10, chargeinf=0.002, exf=2.0e6)
     m = ek.MultiSimulation(p, list(range(n)))
     m.init()
-    m.step(4)
-    ms = m.step_timed(steps)
     cells = p.NX * p.NY * p.NZ
-    print(json.dumps({"driver": "ek_multi (one process, peer copies, events)", "n_gpus": n, "grid": [p.NX, p.NY, p.NZ],
-                      "steps": steps, "ms_per_step": round(ms / steps, 3),
-                      "mlups": round(cells * steps / (ms * 1e-3) / 1e6, 1)}), flush=True)
+    for pipeline in (1, 0):
+        m.L.ek_multi_set_pipeline(m.h, pipeline)
+        m.step(4)
+        ms = m.step_timed(steps)
+        print(json.dumps({"driver": "ek_multi (one process, peer copies, events)", "pipeline": pipeline, "n_gpus": n,
+                          "grid": [p.NX, p.NY, p.NZ], "steps": steps, "ms_per_step": round(ms / steps, 3),
+                          "mlups": round(cells * steps / (ms * 1e-3) / 1e6, 1)}), flush=True)
     m.close()
     assert same
 
