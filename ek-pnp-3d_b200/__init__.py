@@ -144,6 +144,9 @@ def load_library():
         getattr(L, name).argtypes = [H]
     L.ek_multi_step.argtypes = [H, C.c_int]
     L.ek_multi_set_pipeline.argtypes = [H, C.c_int]
+    L.ek_multi_read_data.argtypes = [H, C.c_char_p, C.POINTER(C.c_double)]
+    L.ek_multi_checkpoint_save.argtypes = [H, C.c_char_p, C.c_double]
+    L.ek_multi_checkpoint_load.argtypes = [H, C.c_char_p, C.POINTER(C.c_double)]
     L.ek_multi_step_timed.argtypes = [H, C.c_int, C.POINTER(C.c_float)]
     L.ek_multi_get_field.argtypes = [H, C.c_int, C.c_void_p]
     L.ek_multi_set_fields.argtypes = [H, C.POINTER(C.c_void_p)]
@@ -432,3 +435,16 @@ class MultiSimulation:
 
     def fields(self) -> dict:
         return {n: self.field(n) for n in FIELDS}
+
+    def checkpoint_save(self, path: str, time: float = 0.0):
+        self._ck(self.L.ek_multi_checkpoint_save(self.h, path.encode(), float(time)), "ek_multi_checkpoint_save")
+
+    def checkpoint_load(self, path: str) -> float:
+        t = C.c_double()
+        self._ck(self.L.ek_multi_checkpoint_load(self.h, path.encode(), C.byref(t)), "ek_multi_checkpoint_load")
+        return t.value
+
+    def read_data(self, path: str) -> float:
+        t = C.c_double()
+        self._ck(self.L.ek_multi_read_data(self.h, path.encode(), C.byref(t)), "ek_multi_read_data")
+        return t.value

@@ -77,3 +77,12 @@ struct EkDumpGrid {
 void ek_io_extrapolate_walls(EkHostFields &H, int NX, int NY, int NZ);
 bool ek_io_write_tecplot(const char *path, const EkDumpGrid &g, const EkHostFields &H, double time, int append, int first);
 bool ek_io_write_end(const char *path, const EkDumpGrid &g, const EkHostFields &H, double time);
+bool ek_io_read_end(const char *path, size_t cells, EkHostFields &H, double *time, std::string &err);
+// header of the binary checkpoint (then 11 fields, then 4 sets x 27 x cells pre-collision populations,
+// all in the reference's natural order over the WHOLE domain: single- and multi-GPU runs share the format)
+struct EkCkptHeader {
+    char magic[8];        // "EKB200C1"
+    int NX, NY, NZ, nfields;
+    long long steps;
+    double time;
+};

@@ -202,13 +202,13 @@ ek_status ek_save_data_end(ek_handle *h, const char *path, double time)
 // columns per cell in scalar_index order (time ux uy uz rho c+ c- phi Ex Ey Ez T).  As in
 // the reference the macroscopic arrays are restored and the caller re-creates the
 // populations with ek_init_equilibrium() (main.cu:161-176); E is taken from the file.
-ek_status ek_read_data(ek_handle *h, const char *path, double *time)
+}  // extern "C"
+
+// parser of the save_data_end text format; false with `err` set on failure
+bool ek_io_read_end(const char *path, size_t cells, EkHostFields &H, double *time, std::string &err)
 {
-    if (!h || !path) return EK_ERR_INVALID;
     FILE *f = fopen(path, "r");
-    if (!f) { ek_set_error(h, std::string("cannot open ") + path); return EK_ERR_INVALID; }
-    const size_t cells = (size_t)h->c.NX * h->c.NY * h->c.NZ;
-    EkHostFields H;
+    if (!f) { err = std::string("cannot open ") + path; return false; }
     for (int k = 0; k < EK_NFIELDS; ++k) H.f[k].resize(cells);
     double t = 0.0;
     for (size_t i = 0; i < cells; ++i) {
@@ -217,30 +217,34 @@ ek_status ek_read_data(ek_handle *h, const char *path, double *time)
                              &H.f[EK_EX][i], &H.f[EK_EY][i], &H.f[EK_EZ][i], &H.f[EK_T][i]);
         if (n != 12) {
             fclose(f);
-            ek_set_error(h, std::string(path) + ": truncated or malformed restart file (cell " + std::to_string(i) + ")");
-            return EK_ERR_INVALID;
+            err = std::string(path) + ": truncated or malformed restart file (cell " + std::to_string(i) + ")";
+            return false;
         }
     }
     fclose(f);
+    if (time) *time = t;
+    return true;
+}
+
+extern "C" {
+
+ek_status ek_read_data(ek_handle *h, const char *path, double *time)
+{
+    if (!h || !path) return EK_ERR_INVALID;
+    EkHostFields H;
+    std::string err;
+    if (!ek_io_read_end(path, (size_t)h->c.NX * h->c.NY * h->c.NZ, H, time, err)) {
+        ek_set_error(h, err);
+        return EK_ERR_INVALID;
+    }
     const double *ptr[EK_NFIELDS];
     for (int k = 0; k < EK_NFIELDS; ++k) ptr[k] = H.f[k].data();
-    ek_status st = ek_set_fields(h, ptr, 0);
-    if (st != EK_OK) return st;
-    if (time) *time = t;
-    return EK_OK;
+    return ek_set_fields(h, ptr, 0);
 }
 
 // ---- exact binary checkpoint: header, 11 fields, c+ - c-, the four population sets in the
 // reference's natural order (27 x cells, pre-collision values) -- independent of the
 // in-place layout, the A-A parity and the slab/ghost padding of the run that wrote it.
-namespace {
-struct CkptHeader {
-    char magic[8];        // "EKB200C1"
-    int NX, NY, NZ, nfields;
-    long long steps;
-    double time;
-};
-}  // namespace
 
 ek_status ek_checkpoint_save(ek_handle *h, const char *path, double time)
 {
@@ -248,7 +252,7 @@ ek_status ek_checkpoint_save(ek_handle *h, const char *path, double time)
     if (!h->pops_ready) { ek_set_error(h, "ek_checkpoint_save before the populations exist"); return EK_ERR_STATE; }
     FILE *f = fopen(path, "wb");
     if (!f) { ek_set_error(h, std::string("cannot open ") + path); return EK_ERR_INVALID; }
-    CkptHeader hd;
+    EkCkptHeader hd;
     memcpy(hd.magic, "EKB200C1", 8);
     hd.NX = h->c.NX; hd.NY = h->c.NY; hd.NZ = h->c.NZ; hd.nfields = EK_NFIELDS;
     hd.steps = h->steps; hd.time = time;
@@ -275,7 +279,7 @@ ek_status ek_checkpoint_load(ek_handle *h, const char *path, double *time)
     if (!h || !path) return EK_ERR_INVALID;
     FILE *f = fopen(path, "rb");
     if (!f) { ek_set_error(h, std::string("cannot open ") + path); return EK_ERR_INVALID; }
-    CkptHeader hd;
+    EkCkptHeader hd;
     if (fread(&hd, sizeof(hd), 1, f) != 1 || memcmp(hd.magic, "EKB200C1", 8) != 0 || hd.NX != h->c.NX ||
         hd.NY != h->c.NY || hd.NZ != h->c.NZ || hd.nfields != EK_NFIELDS) {
         fclose(f);

@@ -212,6 +212,10 @@ ek_status poisson_rest(ek_multi *m, bool join_halo)
     return phi_halo_exchange(m);
 }
 
+// after a checkpoint was loaded into the natural layout (A-A parity 0): the next, even step is
+// node-local and refreshes the population ghosts itself; only phi's ghost columns are needed
+ek_status restore_ghosts(ek_multi *m) { return phi_halo_exchange(m); }
+
 void release(ek_multi *m)
 {
     for (int s = 0; s < (int)m->h.size(); ++s) {
@@ -494,6 +498,110 @@ ek_status ek_multi_save_data_end(ek_multi *m, const char *path, double time)
     if (st != EK_OK) return st;
     const EkDumpGrid g = {m->global.NX, m->global.NY, m->global.NZ, m->global.dx, m->global.dy, m->global.dz};
     if (!ek_io_write_end(path, g, H, time)) { m->err = std::string("cannot open ") + path; return EK_ERR_INVALID; }
+    return EK_OK;
+}
+
+// ---- restart of the whole domain: the reference's text file and the exact checkpoint, in the
+// formats of ek_read_data / ek_checkpoint_* (a single-GPU file restarts a multi-GPU run and back)
+ek_status ek_multi_read_data(ek_multi *m, const char *path, double *time)
+{
+    if (!m || !path) return EK_ERR_INVALID;
+    EkHostFields H;
+    if (!ek_io_read_end(path, (size_t)m->global.NX * m->global.NY * m->global.NZ, H, time, m->err)) return EK_ERR_INVALID;
+    const double *ptr[EK_NFIELDS];
+    for (int k = 0; k < EK_NFIELDS; ++k) ptr[k] = H.f[k].data();
+    return ek_multi_set_fields(m, ptr);
+}
+
+ek_status ek_multi_checkpoint_save(ek_multi *m, const char *path, double time)
+{
+    if (!m || !path) return EK_ERR_INVALID;
+    if (!m->pops) { m->err = "ek_multi_checkpoint_save before the populations exist"; return EK_ERR_STATE; }
+    FILE *f = fopen(path, "wb");
+    if (!f) { m->err = std::string("cannot open ") + path; return EK_ERR_INVALID; }
+    const int NXg = m->global.NX, NXl = NXg / m->P, NY = m->global.NY, NZ = m->global.NZ;
+    const size_t cells = (size_t)NXg * NY * NZ, lcells = (size_t)NXl * NY * NZ, rows = (size_t)NY * NZ;
+    EkCkptHeader hd;
+    memcpy(hd.magic, "EKB200C1", 8);
+    hd.NX = NXg; hd.NY = NY; hd.NZ = NZ; hd.nfields = EK_NFIELDS;
+    hd.steps = m->h[0]->steps; hd.time = time;
+    bool ok = fwrite(&hd, sizeof(hd), 1, f) == 1;
+    ek_status st = EK_OK;
+    std::vector<double> g(cells), l(27 * lcells);
+    for (int k = 0; k < EK_NFIELDS && ok && st == EK_OK; ++k) {
+        st = ek_multi_get_field(m, k, g.data());
+        ok = st == EK_OK && fwrite(g.data(), sizeof(double), cells, f) == cells;
+    }
+    // populations: one direction of the whole domain at a time would need 27 passes over the slabs;
+    // instead one set at a time (27 x cells doubles on the host)
+    std::vector<double> gp;
+    for (int set = 0; set < EK_NSETS && ok && st == EK_OK; ++set) {
+        gp.resize(27 * cells);
+        for (int s = 0; s < m->P && st == EK_OK; ++s) {
+            st = ek_get_populations(m->h[s], set, l.data(), 0);
+            if (st != EK_OK) { fail(m, m->h[s], "ek_get_populations", st); break; }
+            for (int d = 0; d < 27; ++d)
+                for (size_t r = 0; r < rows; ++r)
+                    memcpy(gp.data() + (size_t)d * cells + r * NXg + (size_t)s * NXl, l.data() + (size_t)d * lcells + r * NXl,
+                           (size_t)NXl * sizeof(double));
+        }
+        ok = st == EK_OK && fwrite(gp.data(), sizeof(double), 27 * cells, f) == 27 * cells;
+    }
+    fclose(f);
+    if (st != EK_OK) return st;
+    if (!ok) { m->err = std::string("short write to ") + path; return EK_ERR_INVALID; }
+    return EK_OK;
+}
+
+ek_status ek_multi_checkpoint_load(ek_multi *m, const char *path, double *time)
+{
+    if (!m || !path) return EK_ERR_INVALID;
+    FILE *f = fopen(path, "rb");
+    if (!f) { m->err = std::string("cannot open ") + path; return EK_ERR_INVALID; }
+    const int NXg = m->global.NX, NXl = NXg / m->P, NY = m->global.NY, NZ = m->global.NZ;
+    const size_t cells = (size_t)NXg * NY * NZ, lcells = (size_t)NXl * NY * NZ, rows = (size_t)NY * NZ;
+    EkCkptHeader hd;
+    if (fread(&hd, sizeof(hd), 1, f) != 1 || memcmp(hd.magic, "EKB200C1", 8) != 0 || hd.NX != NXg || hd.NY != NY ||
+        hd.NZ != NZ || hd.nfields != EK_NFIELDS) {
+        fclose(f);
+        m->err = std::string(path) + ": not a checkpoint of this grid";
+        return EK_ERR_INVALID;
+    }
+    EkHostFields H;
+    bool ok = true;
+    for (int k = 0; k < EK_NFIELDS && ok; ++k) {
+        H.f[k].resize(cells);
+        ok = fread(H.f[k].data(), sizeof(double), cells, f) == cells;
+    }
+    ek_status st = EK_OK;
+    if (ok) {
+        const double *ptr[EK_NFIELDS];
+        for (int k = 0; k < EK_NFIELDS; ++k) ptr[k] = H.f[k].data();
+        st = ek_multi_set_fields(m, ptr);
+    }
+    std::vector<double> gp(27 * cells), l(27 * lcells);
+    for (int set = 0; set < EK_NSETS && ok && st == EK_OK; ++set) {
+        ok = fread(gp.data(), sizeof(double), 27 * cells, f) == 27 * cells;
+        for (int s = 0; s < m->P && ok && st == EK_OK; ++s) {
+            for (int d = 0; d < 27; ++d)
+                for (size_t r = 0; r < rows; ++r)
+                    memcpy(l.data() + (size_t)d * lcells + r * NXl, gp.data() + (size_t)d * cells + r * NXg + (size_t)s * NXl,
+                           (size_t)NXl * sizeof(double));
+            st = ek_set_populations(m->h[s], set, l.data());
+            if (st != EK_OK) fail(m, m->h[s], "ek_set_populations", st);
+        }
+    }
+    fclose(f);
+    if (st != EK_OK) return st;
+    if (!ok) { m->err = std::string(path) + ": truncated checkpoint"; return EK_ERR_INVALID; }
+    for (int s = 0; s < m->P; ++s) {
+        MK(m, m->h[s], ek_populations_restored(m->h[s]));
+        m->h[s]->steps = hd.steps;
+    }
+    // the ghost columns are not part of the file: the face populations of the natural layout and phi
+    MK(m, nullptr, restore_ghosts(m));
+    m->pops = true;
+    if (time) *time = hd.time;
     return EK_OK;
 }
 

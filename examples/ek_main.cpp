@@ -11,7 +11,7 @@
 //             [--ext V/m] [--exf N/m3] [--uw m/s] [--th K] [--cinf mol] [--pb-iters N]
 //             [--restart 0|1] [--checkpoint file] [--resume file] [--device d] [--gpus N]
 // Without --restart the program asks on stdin like main.cu:158-159.  --gpus N splits the domain into
-// N x-slabs on devices 0..N-1 of this process (ek_multi_*, NX must be divisible by 2N; new runs only).
+// N x-slabs on devices 0..N-1 of this process (ek_multi_*, NX must be divisible by 2N).
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -86,7 +86,6 @@ int main(int argc, char **argv)
     ek_handle *h = nullptr;
     Sim sim;
     if (gpus > 1) {
-        if (ckpt_in || ckpt_out || restart == 1) { fprintf(stderr, "--gpus: restart files are single-GPU for now\n"); return 2; }
         int devs[16];
         const int ndev = ek_device_count() > 0 ? ek_device_count() : 1;
         if (gpus > 16) gpus = 16;
@@ -94,7 +93,6 @@ int main(int argc, char **argv)
         ek_status st = ek_multi_create(&P, gpus, devs, 0, &sim.m);
         if (st != EK_OK) die(nullptr, "ek_multi_create (NX divisible by 2*gpus, <= 16 CUDA devices of one node)", st);
         g_multi = sim.m;
-        restart = 0;
     } else {
         ek_status st = ek_create(&P, device, &h);
         if (st != EK_OK) die(nullptr, "ek_create (a CUDA device is required, there is no CPU path)", st);
@@ -105,7 +103,7 @@ int main(int argc, char **argv)
     double t = 0.0;
     if (ckpt_in) {
         printf("Resuming from checkpoint %s...\n", ckpt_in);
-        CK(ek_checkpoint_load(h, ckpt_in, &t));
+        CK(sim.m ? ek_multi_checkpoint_load(sim.m, ckpt_in, &t) : ek_checkpoint_load(h, ckpt_in, &t));
     } else {
         if (restart < 0) {
             printf("Read previous data: Press 1. Start a new simulation: Press 0.\n ");   // main.cu:158
@@ -113,7 +111,7 @@ int main(int argc, char **argv)
         }
         if (restart == 1) {
             printf("Reading previous data...\n");                                          // main.cu:162
-            CK(ek_read_data(h, "data_end.dat", &t));
+            CK(sim.m ? ek_multi_read_data(sim.m, "data_end.dat", &t) : ek_read_data(h, "data_end.dat", &t));
         } else {
             printf("Initializing...\n");                                                    // main.cu:166
             CK(sim.init_fields());                                                          // main.cu:169
@@ -165,7 +163,7 @@ int main(int argc, char **argv)
     CK(sim.tecplot("data.dat", t, 1, 1));                                                   // main.cu:253
     fclose(fumax);
     CK(sim.save_end("data_end.dat", t));                                                    // main.cu:256-257
-    if (ckpt_out) CK(ek_checkpoint_save(h, ckpt_out, t));
+    if (ckpt_out) CK(sim.m ? ek_multi_checkpoint_save(sim.m, ckpt_out, t) : ek_checkpoint_save(h, ckpt_out, t));
     if (sim.m) ek_multi_destroy(sim.m); else ek_destroy(h);
     return 0;
 }

@@ -286,6 +286,11 @@ ek_status ek_multi_wall_current(ek_multi *m, double *current);
 ek_status ek_multi_max_uz(ek_multi *m, double *umax);
 ek_status ek_multi_save_data_tecplot(ek_multi *m, const char *path, double time, int append, int first);
 ek_status ek_multi_save_data_end(ek_multi *m, const char *path, double time);
+/* restart of the whole domain in the formats of ek_read_data / ek_checkpoint_* (files are interchangeable
+ * between single- and multi-GPU runs; one population set at a time is staged in host memory) */
+ek_status ek_multi_read_data(ek_multi *m, const char *path, double *time);
+ek_status ek_multi_checkpoint_save(ek_multi *m, const char *path, double time);
+ek_status ek_multi_checkpoint_load(ek_multi *m, const char *path, double *time);
 ek_status ek_multi_set_pipeline(ek_multi *m, int on);   /* 1: overlap streams (default), 0: in sequence */
 int ek_multi_slabs(ek_multi *m);
 ek_handle *ek_multi_slab(ek_multi *m, int s);
