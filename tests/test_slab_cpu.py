@@ -80,6 +80,19 @@ def oracle_case():
     return p, f["charge"] - f["chargen"], o.field("phi").copy()
 
 
+def test_local_transport_fills_preallocated_receive_buffers():
+    slab = slab_mod()
+    P = 3
+    comm = slab.LocalComm(P)
+    send = [torch.stack([torch.full((2,), 10.0 * r + i) for i in range(P)]) for r in range(P)]
+    recv = [torch.zeros_like(s) for s in send]
+    out = comm.all_to_all(send, recv)
+    for r in range(P):
+        assert out[r] is recv[r]
+        for i in range(P):
+            assert bool((recv[r][i] == 10.0 * i + r).all())
+
+
 @pytest.mark.parametrize("P", [1, 2, 3, 4])
 def test_local_transport_matches_the_oracle(P):
     slab = slab_mod()
@@ -108,6 +121,12 @@ def _worker(rank, world, port, q):
         got = run_distributed_poisson(slab, comm, p, {rank: dq[:, :, a:b]}, [rank])[rank]
         err = float(np.abs(got - phi[1:-1, :, a:b]).max() / np.abs(phi).max())
         m = comm.max_over_ranks(float(rank))
+        # all-to-all into preallocated chunk buffers (what the native Poisson stage hands to the transport):
+        # part i of my send buffer must arrive as part `rank` of rank i's receive buffer
+        send = torch.stack([torch.full((3,), 100.0 * rank + i, dtype=torch.complex128) for i in range(world)])
+        recv = torch.zeros_like(send)
+        comm.all_to_all_finish(comm.all_to_all_start([send], [recv]))
+        ok = ok and all(bool((recv[i] == 100.0 * i + rank).all()) for i in range(world))
         q.put((rank, ok, err, m))
     finally:
         dist.destroy_process_group()
