@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""Small runs of every kernel family for compute-sanitizer (memcheck):
+"""Small runs of every kernel family (a smoke run; written for compute-sanitizer memcheck, which is
+closed on this GPU pool):
 single domain (general + lean path, both A-A parities, field output, push mode), Poisson paths,
 start-up, x-slabs through slab.py (LocalComm, all transports) and through ek_multi."""
 import importlib
@@ -39,4 +40,4 @@ m.init()
 m.step(3)
 m.fields()
 m.close()
-print("memcheck cases done")
+print("all kernel families ran")
