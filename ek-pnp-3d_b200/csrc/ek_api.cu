@@ -276,6 +276,10 @@ ek_status ek_set_option(ek_handle *h, const char *key, long long value)
     }
     if (!strcmp(key, "zchunk")) {
         if (value != 0 && value < 2) return EK_ERR_INVALID;  // the owner of z = 0 must own z = 1
+        if (h->sp.ready) {   // the chunks of the distributed Poisson stage are groups of z-blocks of this size
+            ek_set_error(h, "zchunk cannot change after ek_slab_poisson_setup");
+            return EK_ERR_STATE;
+        }
         h->zchunk = value == 0 ? ek_auto_zchunk(h->c) : (int)value;   // 0: automatic
         return EK_OK;
     }
