@@ -271,6 +271,7 @@ ek_status ek_set_option(ek_handle *h, const char *key, long long value)
     if (!strcmp(key, "stream_mode")) {
         if (h->allocated) { ek_set_error(h, "stream_mode must be set before the first init/set_fields"); return EK_ERR_STATE; }
         if (value != EK_STREAM_AA && value != EK_STREAM_PUSH) return EK_ERR_INVALID;
+        if (h->slab && value != EK_STREAM_AA) { ek_set_error(h, "x-slabs use the A-A scheme (halo phases, ek_slab.cu)"); return EK_ERR_STATE; }
         h->stream_mode = (int)value;
         return EK_OK;
     }
@@ -351,9 +352,19 @@ ek_status ek_reset_counters(ek_handle *h)
     return EK_OK;
 }
 
+// single-domain entry points on a slab of a multi-rank domain would solve a Poisson problem that is
+// periodic over the LOCAL width: refuse instead of computing something silently wrong
+static bool refuse_on_slab(ek_handle *h, const char *what)
+{
+    if (h->nranks <= 1) return false;
+    ek_set_error(h, std::string(what) + ": x-slab of a multi-rank domain -- use ek_rank_* / ek_multi_* (distributed Poisson stage)");
+    return true;
+}
+
 ek_status ek_init_fields(ek_handle *h)
 {
     if (!h) return EK_ERR_INVALID;
+    if (refuse_on_slab(h, "ek_init_fields")) return EK_ERR_STATE;
     DeviceGuard g(h->device);
     ek_status st = ek_alloc_state(h);
     if (st != EK_OK) return st;
@@ -419,6 +430,8 @@ ek_status ek_init_equilibrium(ek_handle *h)
 
 ek_status ek_init(ek_handle *h)
 {
+    if (!h) return EK_ERR_INVALID;
+    if (refuse_on_slab(h, "ek_init")) return EK_ERR_STATE;
     ek_status st = ek_init_fields(h);
     if (st != EK_OK) return st;
     return ek_init_equilibrium(h);
@@ -495,6 +508,7 @@ ek_status ek_fast_poisson(ek_handle *h, int write_efield)
 ek_status ek_step(ek_handle *h, int nsteps)
 {
     if (!h || nsteps < 0) return EK_ERR_INVALID;
+    if (refuse_on_slab(h, "ek_step")) return EK_ERR_STATE;
     for (int i = 0; i < nsteps; ++i) {
         const int full = (i == nsteps - 1);
         ek_status st = ek_stream_collide_save(h, full);

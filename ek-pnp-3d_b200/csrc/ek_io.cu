@@ -133,6 +133,7 @@ ek_status ek_wall_current(ek_handle *h, double *current)
 {
     if (!h || !current) return EK_ERR_INVALID;
     if (!h->allocated) return EK_ERR_STATE;
+    DeviceGuard g(h->device);
     const EkConst &c = h->c;
     if (h->efield_stale) {
         ek_launch_efield(c, h->fld[EK_PHI], h->fld[EK_EX], h->fld[EK_EY], h->fld[EK_EZ], h->stream);
@@ -156,6 +157,7 @@ ek_status ek_max_uz(ek_handle *h, double *umax)
 {
     if (!h || !umax) return EK_ERR_INVALID;
     if (!h->allocated) return EK_ERR_STATE;
+    DeviceGuard g(h->device);
     const EkConst &c = h->c;
     const size_t n = (size_t)c.NY * c.NZ;
     double *partial = nullptr;

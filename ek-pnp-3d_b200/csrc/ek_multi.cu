@@ -380,6 +380,7 @@ ek_status ek_multi_step(ek_multi *m, int nsteps)
         }
         if (full)
             for (int s = 0; s < m->P; ++s) MK(m, m->h[s], ek_compute_efield(m->h[s]));
+        for (int s = 0; s < m->P; ++s) m->h[s]->steps += 1;   // what ek_multi_checkpoint_save writes
     }
     return EK_OK;
 }

@@ -454,13 +454,14 @@ class SlabGroup:
         self.back_stream.wait_stream(main)
         self._phi_ready = []
         with self._on_stream(self.back_stream):
+            # wall planes first (only when something other than the solver wrote phi): the ghost columns
+            # of plane 0 travel with chunk 0 and the next step's first LBM launches read them
+            for s in self.slabs:
+                s.ck(s.L.ek_poisson_finish(s.h, 0), "ek_poisson_finish")
             for k in range(self.K):
                 finish(landed[k])
                 for s in self.slabs:
                     s.ck(s.L.ek_slab_poisson_backward(s.h, k), "ek_slab_poisson_backward")
-                if k == self.K - 1:
-                    for s in self.slabs:
-                        s.ck(s.L.ek_poisson_finish(s.h, 0), "ek_poisson_finish")
                 z0, z1 = self._chunk_planes(k)
                 self.phi_halo_exchange_range(z0, z1)
                 ev = torch.cuda.Event()

@@ -11,10 +11,16 @@ import pytest
 from oracle import ek_oracle as eo
 from tests import util
 
-# per-field-group tolerances (max|a-b|/max|b|).  The velocity is a difference of
-# populations of size ~1e2 that cancel to ~1e-5: one ulp of a population is
-# ~1e-9 of max|u|, so 1e-7 is the honest bound for u (DESIGN.md "Tolerances").
-TOL = {"rho": 1e-12, "charge": 1e-12, "chargen": 1e-12, "phi": 1e-12, "T": 1e-12, "E": 1e-12, "u": 1e-7}
+# per-field-group tolerances (max|a-b|/max|b|): the north star's 1e-12 for every field.  The
+# velocity gets the same relative 1e-12 PLUS an absolute floor of K_U ulps of the largest fluid
+# population expressed as a velocity (tests/util.py u_ulp: 5.7e-15 m/s for rho0 = 1000, CFL = 0.01):
+#     max|du| <= 1e-12 * max|u| + K_U * ulp(w0 * rho) / (CFL * rho)
+# u is a difference of populations of size 3e2 that cancel to <= 1e-5, so implementations whose
+# populations differ in the last bit differ in u by a few of these units however small u is.
+# K_U bounds what the tests measure (DESIGN.md section 6 records the measured values: <= 24 ulps
+# against the reference's CUDA build after up to 1000 steps).
+TOL = {"rho": 1e-12, "charge": 1e-12, "chargen": 1e-12, "phi": 1e-12, "T": 1e-12, "E": 1e-12, "u": 1e-12}
+K_U = 64.0
 
 
 def load_golden(name):
@@ -26,8 +32,11 @@ def load_golden(name):
     return z, meta
 
 
-def check(err: dict, tol=TOL, scale=1.0):
-    bad = {k: v for k, v in err.items() if not v <= tol[k] * scale}
+def check(err: dict, tol=TOL, scale=1.0, k_u=K_U):
+    bad = {k: v for k, v in err.items() if k in tol and k != "u" and not v <= tol[k] * scale}
+    if "u_abs" in err:
+        if not err["u_abs"] <= tol["u"] * scale * err["u_scale"] + k_u * err["u_ulp"]:
+            bad["u"] = f"|du| = {err['u_abs']:.3e} = {err['u_ulps']:.1f} ulps of a population > 1e-12*max|u| + {k_u} ulps"
     assert not bad, f"out of tolerance: {bad} (all: {err})"
 
 
@@ -97,7 +106,7 @@ def test_shipped_case_profile():
     # uy, Ex, Ey are pure round-off in this x-y uniform case: compare what is physical
     for k in ("rho", "charge", "chargen", "phi", "T"):
         assert err[k] < 1e-11, err
-    assert np.abs(got["ux"] - want["ux"]).max() <= 1e-7 * np.abs(want["ux"]).max()
+    assert err["u_abs"] <= 1e-12 * err["u_scale"] + K_U * err["u_ulp"], err
     assert np.abs(got["Ez"] - want["Ez"]).max() <= 1e-11 * np.abs(want["Ez"]).max()
 
 

@@ -68,7 +68,7 @@ def read_pops(path: str, shape) -> np.ndarray:
 
 
 def run_ref(case: str, steps: int, perturb: float = 0.0, init_fields: dict | None = None, pops: bool = False,
-            extra=(), dc: bool = False):
+            extra=(), dc: bool = False, dump_init: bool = True):
     """Run the reference's own CUDA build (oracle/_ref) and return
     (init_fields, final_fields, pops or None, info json); info["dc"] holds the
     per-step forward DC coefficients when dc=True."""
@@ -77,8 +77,9 @@ def run_ref(case: str, steps: int, perturb: float = 0.0, init_fields: dict | Non
     shape = (cp["NZ"], cp["NY"], cp["NX"])
     exe = os.path.join(REF_DIR, f"ek_ref_{case}")
     with tempfile.TemporaryDirectory(prefix="ekref_run_") as tmp:
-        cmd = [exe, "--steps", str(steps), "--dump-init", os.path.join(tmp, "init.bin"),
-               "--dump-final", os.path.join(tmp, "final.bin")]
+        cmd = [exe, "--steps", str(steps), "--dump-final", os.path.join(tmp, "final.bin")]
+        if dump_init:
+            cmd += ["--dump-init", os.path.join(tmp, "init.bin")]
         if perturb:
             cmd += ["--perturb", repr(perturb)]
         if init_fields is not None:
@@ -93,19 +94,32 @@ def run_ref(case: str, steps: int, perturb: float = 0.0, init_fields: dict | Non
         info = json.loads(out.strip().splitlines()[-1])
         if dc:
             info["dc"] = np.fromfile(os.path.join(tmp, "dc.bin"), dtype=np.float64)
-        init = read_fields(os.path.join(tmp, "init.bin"), shape)
+        init = read_fields(os.path.join(tmp, "init.bin"), shape) if dump_init else init_fields
         final = read_fields(os.path.join(tmp, "final.bin"), shape)
         p = read_pops(os.path.join(tmp, "pops.bin"), shape) if pops else None
     return init, final, p, info
 
 
+def u_ulp(ref: dict, cfl: float = 0.01) -> float:
+    """One ulp of the largest fluid population expressed as a velocity.  u = (sum_d c_d f_d / CFL +
+    F dt/2) / rho (LBM.cu:639-644) is a difference of populations of size w0*rho ~ 3e2 that cancel
+    to ~1e-5 or less, so an implementation that is not bit-identical in every population (FMA
+    contraction, FFT order) differs in u by a few of these, whatever max|u| is."""
+    rho = float(np.abs(ref["rho"]).max())
+    return float(np.spacing(8.0 / 27.0 * rho)) / (cfl * rho)
+
+
 def field_errors(a: dict, b: dict) -> dict:
-    """max|a-b| / max|b| per field group (components of a vector share the scale)."""
+    """max|a-b| / max|b| per field group (components of a vector share the scale); for the velocity
+    also the absolute error, its scale and the error in units of u_ulp()."""
     out = {}
     for g, names in GROUPS.items():
         scale = max(float(np.abs(b[n]).max()) for n in names)
         err = max(float(np.abs(np.asarray(a[n]) - np.asarray(b[n])).max()) for n in names)
         out[g] = err / scale if scale > 0 else err
+        if g == "u":
+            out["u_abs"], out["u_scale"], out["u_ulp"] = err, scale, u_ulp(b)
+            out["u_ulps"] = err / out["u_ulp"]
     return out
 
 
