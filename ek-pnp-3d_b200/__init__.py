@@ -19,6 +19,9 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("EK_B200_LIB") or os.path.join(_HERE, "libek_b200.so")  # override: development A/B builds
+# the same sources built with -DEK_XCHECK (slower kernel variants, literal odd-extension Poisson transform):
+# what the parity tests cross-check the product against; never loaded by the product path
+XCHECK_LIB_PATH = os.path.join(_HERE, "libek_b200_xcheck.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "ek_b200.h")
 
 FIELDS = ("rho", "ux", "uy", "uz", "charge", "chargen", "phi", "T", "Ex", "Ey", "Ez")
@@ -58,19 +61,19 @@ class Params(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
-_lib = None
+_libs = {}
 
 
-def load_library():
-    """Load libek_b200.so; fail loudly if it has not been built."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
+def load_library(path: str | None = None):
+    """Load libek_b200.so (or another build of it); fail loudly if it has not been built."""
+    path = path or LIB_PATH
+    if path in _libs:
+        return _libs[path]
+    if not os.path.exists(path):
         raise EkError(
-            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "or `make -C ek-pnp-3d_b200/csrc`. There is no CPU fallback.")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(path)
     H = C.c_void_p
     L.ek_abi_version.restype = C.c_int
     L.ek_device_count.restype = C.c_int
@@ -154,7 +157,7 @@ def load_library():
     L.ek_multi_slab.restype = C.c_void_p
     L.ek_multi_last_error.argtypes = [H]
     L.ek_multi_last_error.restype = C.c_char_p
-    _lib = L
+    _libs[path] = L
     return L
 
 
@@ -179,10 +182,11 @@ class Simulation:
     """One coupled EK-PNP simulation on one CUDA device."""
 
     def __init__(self, params: Params | None = None, device: int = -1, stream_mode: int | None = None,
-                 zchunk: int | None = None, profile: bool = False, slab: tuple | None = None):
+                 zchunk: int | None = None, profile: bool = False, slab: tuple | None = None, xcheck: bool = False):
         """slab=(rank, nranks): this handle owns the x-slab `rank` of the global
-        domain described by `params` (multi-GPU path, see slab.py)."""
-        self.L = load_library()
+        domain described by `params` (multi-GPU path, see slab.py).  xcheck=True (tests only)
+        runs on the cross-check build libek_b200_xcheck.so."""
+        self.L = load_library(XCHECK_LIB_PATH if xcheck else None)
         self.p = params if params is not None else default_params()
         self.h = C.c_void_p()
         self.device = int(device)

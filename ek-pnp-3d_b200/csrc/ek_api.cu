@@ -189,6 +189,16 @@ extern "C" {
 
 int ek_abi_version(void) { return EK_B200_ABI_VERSION; }
 
+// 1: this is the cross-check build (extra kernel variants, Poisson path 1), 0: the product library
+int ek_is_xcheck_build(void)
+{
+#ifdef EK_XCHECK
+    return 1;
+#else
+    return 0;
+#endif
+}
+
 int ek_device_count(void)
 {
     int n = 0;
@@ -256,6 +266,7 @@ ek_status ek_destroy(ek_handle *h)
     DeviceGuard g(h->device);
     cudaStreamSynchronize(h->stream);
     collect_events(h);
+    if (h->pair_graph) cudaGraphExecDestroy(h->pair_graph);
     free_state(h);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -268,6 +279,12 @@ void *ek_stream(ek_handle *h) { return h ? (void *)h->stream : nullptr; }
 ek_status ek_set_option(ek_handle *h, const char *key, long long value)
 {
     if (!h || !key) return EK_ERR_INVALID;
+    h->epoch += 1;   // whatever changes may be baked into the step graph
+    if (!strcmp(key, "graph")) {
+        if (value < -1 || value > 1) return EK_ERR_INVALID;
+        h->graph_opt = (int)value;
+        return EK_OK;
+    }
     if (!strcmp(key, "stream_mode")) {
         if (h->allocated) { ek_set_error(h, "stream_mode must be set before the first init/set_fields"); return EK_ERR_STATE; }
         if (value != EK_STREAM_AA && value != EK_STREAM_PUSH) return EK_ERR_INVALID;
@@ -289,11 +306,17 @@ ek_status ek_set_option(ek_handle *h, const char *key, long long value)
         // 0: four warps, lean deep-interior path (default); 1: eight warps; 2: five warps;
         // 3: four warps, general path everywhere (cross-check of the lean path)
         if (value < 0 || value > 3) return EK_ERR_INVALID;
+#ifndef EK_XCHECK
+        if (value == 1 || value == 2) { ek_set_error(h, "kernel variants 1/2 are only in the cross-check build libek_b200_xcheck.so"); return EK_ERR_INVALID; }
+#endif
         h->kernel = (int)value;
         return EK_OK;
     }
     if (!strcmp(key, "poisson_path")) {
         if (value != 0 && value != 1) return EK_ERR_INVALID;
+#ifndef EK_XCHECK
+        if (value == 1) { ek_set_error(h, "Poisson path 1 is only in the cross-check build libek_b200_xcheck.so"); return EK_ERR_INVALID; }
+#endif
         h->poisson_path = (int)value;
         return EK_OK;
     }
@@ -304,8 +327,12 @@ ek_status ek_set_option(ek_handle *h, const char *key, long long value)
 ek_status ek_set_poisson_dc(ek_handle *h, int mode, double ghat0)
 {
     if (!h || mode < EK_DC_ZERO || mode > EK_DC_PRESCRIBED) return EK_ERR_INVALID;
+#ifndef EK_XCHECK
+    if (mode == EK_DC_LITERAL) { ek_set_error(h, "EK_DC_LITERAL needs the odd-extension transform of the cross-check build libek_b200_xcheck.so"); return EK_ERR_INVALID; }
+#endif
     h->dc_mode = mode;
     h->dc_ghat0 = ghat0;
+    h->epoch += 1;
     return EK_OK;
 }
 
@@ -322,6 +349,7 @@ ek_status ek_get_counter(ek_handle *h, const char *key, double *value)
     if (!h || !key || !value) return EK_ERR_INVALID;
     DeviceGuard g(h->device);
     if (!strcmp(key, "steps")) { *value = (double)h->steps; return EK_OK; }
+    if (!strcmp(key, "graph_replays")) { *value = (double)h->graph_replays; return EK_OK; }
     if (!strcmp(key, "zchunk")) { *value = (double)h->zchunk; return EK_OK; }
     if (!strcmp(key, "lbm_launches")) { *value = (double)h->lbm_launches; return EK_OK; }
     if (!strcmp(key, "poisson_launches")) { *value = (double)h->poisson_launches; return EK_OK; }
@@ -462,9 +490,12 @@ ek_status ek_stream_collide_save_range(ek_handle *h, int write_fields, int zbloc
         EK_CUDA(h, cudaEventCreate(&e0)); EK_CUDA(h, cudaEventCreate(&e1));
         EK_CUDA(h, cudaEventRecord(e0, h->stream));
     }
+#ifdef EK_XCHECK
     if (h->kernel == 1) EK_CUDA(h, ek_launch_step8(a, mode, write_fields != 0, h->e_from_arrays, h->stream));
     else if (h->kernel == 2) EK_CUDA(h, ek_launch_step5(a, mode, write_fields != 0, h->e_from_arrays, h->stream));
-    else EK_CUDA(h, ek_launch_step(a, mode, write_fields != 0, h->e_from_arrays, h->kernel != 3, h->stream));
+    else
+#endif
+    EK_CUDA(h, ek_launch_step(a, mode, write_fields != 0, h->e_from_arrays, h->kernel != 3, h->stream));
     if (h->profile) {
         EK_CUDA(h, cudaEventRecord(e1, h->stream));
         h->ev_lbm.emplace_back(e0, e1);
@@ -505,17 +536,76 @@ ek_status ek_fast_poisson(ek_handle *h, int write_efield)
     return EK_OK;
 }
 
+static ek_status one_step(ek_handle *h, int full)
+{
+    ek_status st = ek_stream_collide_save(h, full);
+    if (st != EK_OK) return st;
+    st = ek_fast_poisson(h, full);
+    if (st != EK_OK) return st;
+    h->steps += 1;
+    return EK_OK;
+}
+
+// may the next two (non-final) steps run as one graph launch?
+static bool graph_usable(ek_handle *h)
+{
+    const bool want = h->graph_opt == 1 || (h->graph_opt == -1 && (long long)h->c.NX * h->c.NY * h->c.NZ < (1LL << 22));
+    // (plans and scratch of the Poisson path in use exist: nothing may allocate during the capture;
+    // the legacy default stream of the shim cannot be captured)
+    const bool path1 = h->poisson_path == 1 || h->dc_mode == EK_DC_LITERAL;
+    return want && !h->profile && h->dc_mode != EK_DC_PRESCRIBED && !h->e_from_arrays && !h->phi_walls_dirty &&
+           !h->slab && (path1 ? h->poisson.plans : h->poisson.plans2) &&
+           (h->stream_mode == EK_STREAM_PUSH || h->parity == 0) && h->stream != nullptr;
+}
+
+// capture two steps on the handle's stream (nothing executes), instantiate
+static ek_status build_pair_graph(ek_handle *h)
+{
+    if (h->pair_graph) { cudaGraphExecDestroy(h->pair_graph); h->pair_graph = nullptr; }
+    const int parity = h->parity, cur = h->cur;
+    const long long steps = h->steps, l0 = h->lbm_launches, p0 = h->poisson_launches;
+    EK_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
+    ek_status st = one_step(h, 0);
+    if (st == EK_OK) st = one_step(h, 0);
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+    // the capture only recorded: host-side state goes back to where it was
+    h->pair_lbm_launches = h->lbm_launches - l0;
+    h->pair_poisson_launches = h->poisson_launches - p0;
+    h->parity = parity; h->cur = cur; h->steps = steps; h->lbm_launches = l0; h->poisson_launches = p0;
+    if (st != EK_OK) { if (g) cudaGraphDestroy(g); return st; }
+    EK_CUDA(h, e);
+    e = cudaGraphInstantiate(&h->pair_graph, g, 0);
+    cudaGraphDestroy(g);
+    EK_CUDA(h, e);
+    h->graph_epoch = h->epoch;
+    return EK_OK;
+}
+
 ek_status ek_step(ek_handle *h, int nsteps)
 {
     if (!h || nsteps < 0) return EK_ERR_INVALID;
     if (refuse_on_slab(h, "ek_step")) return EK_ERR_STATE;
-    for (int i = 0; i < nsteps; ++i) {
-        const int full = (i == nsteps - 1);
-        ek_status st = ek_stream_collide_save(h, full);
+    DeviceGuard g(h->device);
+    int i = 0;
+    while (i < nsteps) {
+        // the last step of the call writes the macroscopic arrays; pairs of the others replay the graph
+        if (nsteps - 1 - i >= 2 && h->pops_ready && graph_usable(h)) {
+            if (!h->pair_graph || h->graph_epoch != h->epoch) {
+                ek_status st = build_pair_graph(h);
+                if (st != EK_OK) return st;
+            }
+            EK_CUDA(h, cudaGraphLaunch(h->pair_graph, h->stream));
+            h->steps += 2;
+            h->lbm_launches += h->pair_lbm_launches;
+            h->poisson_launches += h->pair_poisson_launches;
+            h->graph_replays += 1;
+            i += 2;
+            continue;
+        }
+        ek_status st = one_step(h, i == nsteps - 1);
         if (st != EK_OK) return st;
-        st = ek_fast_poisson(h, full);
-        if (st != EK_OK) return st;
-        h->steps += 1;
+        ++i;
     }
     return EK_OK;
 }
@@ -552,6 +642,7 @@ ek_status ek_adopt_field(ek_handle *h, int id, double *dev_ptr)
     if (!h->fld_external[id]) cudaFree(h->fld[id]);
     h->fld[id] = dev_ptr;
     h->fld_external[id] = true;
+    h->epoch += 1;
     if (id == EK_PHI) h->phi_walls_dirty = true;
     return EK_OK;
 }

@@ -52,6 +52,15 @@ struct ek_handle {
     int poisson_path = 0;          // 0: xy-FFT + tridiagonal z-solve, 1: odd-extension 3-D FFT
     double dc_ghat0 = 0.0;
 
+    // CUDA graph of a PAIR of coupled steps (even + odd A-A step, or two push steps): small grids are
+    // launch-latency bound (the shipped 50x8x51 case: ~25 us of kernels in a 52 us step), and after a
+    // pair the parity is back where it was, so one instantiated graph replays for the whole run
+    int graph_opt = -1;                    // option "graph": 0 off, 1 on, -1 automatic (grids below 4 M cells)
+    cudaGraphExec_t pair_graph = nullptr;
+    long long epoch = 0, graph_epoch = -1; // anything that changes a baked-in argument bumps `epoch`
+    long long pair_lbm_launches = 0, pair_poisson_launches = 0;
+    long long graph_replays = 0;
+
     // counters / profiling
     bool profile = false;
     long long steps = 0, lbm_launches = 0, poisson_launches = 0;

@@ -34,9 +34,11 @@ struct Sh {
     double cp[32], cn[32], T[32];
     double E[3][32];
     double u[3][32];
+#ifdef EK_XCHECK
     // five-warp variant: partial moments of fluid half A, and rho / F for it
     double rhoA[32], mpA[3][32], mnA[3][32];
     double rho[32], F[3][32];
+#endif
 };
 
 template <int NT> __device__ __forceinline__ void bar_moments() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
@@ -408,6 +410,7 @@ __global__ void __launch_bounds__(128, EK_MIN_CTAS) ek_step_kernel(const __grid_
     else scalar_role<MODE, FULL, EARR, 128, LEAN>(a, sh, role, lane, act, x, y, pi, z0, z1);
 }
 
+#ifdef EK_XCHECK
 // ---------------------------------------------------------------------------
 // Five warps per 32 cells: the fluid set is split over two warps (half A: rest +
 // pairs 1..6, half B: pairs 7..13) because the fluid warp of the four-warp kernel
@@ -536,6 +539,8 @@ __global__ void __launch_bounds__(160, 3) ek_step5_kernel(const __grid_constant_
     else scalar_role<MODE, FULL, EARR, 160>(a, sh, warp - 1, lane, act, x, y, pi, z0, z1);
 }
 
+#endif  // EK_XCHECK
+
 // natural-layout export of the pre-collision state (tests, checkpoints)
 template <int MODE>
 __global__ void ek_export_kernel(const StepArgs a, int s, double *dst)
@@ -585,6 +590,7 @@ __global__ void ek_import_kernel(const StepArgs a, int s, const double *src)
     }
 }
 
+#ifdef EK_XCHECK
 template <int MODE>
 cudaError_t launch_mode5(const StepArgs &a, bool full, bool earr, dim3 grid, cudaStream_t st)
 {
@@ -597,6 +603,7 @@ cudaError_t launch_mode5(const StepArgs &a, bool full, bool earr, dim3 grid, cud
     }
     return cudaGetLastError();
 }
+#endif  // EK_XCHECK
 
 template <int MODE>
 cudaError_t launch_mode(const StepArgs &a, bool full, bool earr, bool lean, dim3 grid, cudaStream_t st)
@@ -628,6 +635,7 @@ cudaError_t ek_launch_step(const StepArgs &a, int mode, bool write_fields, bool 
     }
 }
 
+#ifdef EK_XCHECK
 cudaError_t ek_launch_step5(const StepArgs &a, int mode, bool write_fields, bool e_from_arrays, cudaStream_t st)
 {
     const EkConst &c = a.c;
@@ -638,6 +646,7 @@ cudaError_t ek_launch_step5(const StepArgs &a, int mode, bool write_fields, bool
     default: return launch_mode5<EK_MODE_PUSH>(a, write_fields, e_from_arrays, grid, st);
     }
 }
+#endif  // EK_XCHECK
 
 cudaError_t ek_launch_export(const StepArgs &a, int mode, int set, double *dst, cudaStream_t st)
 {

@@ -237,6 +237,7 @@ __device__ __forceinline__ void efield_lean(const StepArgs &a, const LeanAddr &l
 }
 
 
+#ifdef EK_XCHECK
 // ---- a population set split over two warps: half A = rest + pairs 1..6 (slots
 // 0..12), half B = pairs 7..13 (slots 13..26)
 template <int HALF> struct Half;
@@ -321,5 +322,6 @@ struct FluidPairs8<MODE, 1, 13> {
                                                double, bool, bool, const EkConst &, double *, const Nbr &, bool) {}
 };
 
+#endif  // EK_XCHECK
 
 }  // namespace

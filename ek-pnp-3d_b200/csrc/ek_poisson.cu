@@ -20,7 +20,8 @@
 //    against the sine-transform solution is <= 1e-13 of max|phi| at NZ = 256
 //    (tests/test_parity_gpu.py::test_poisson_paths_agree).
 //
-//  path 1 "odd extension": the reference's own algorithm on a REAL extended
+//  path 1 "odd extension" (cross-check build only, -DEK_XCHECK -> libek_b200_xcheck.so):
+//    the reference's own algorithm on a REAL extended
 //    array of length NE = 2(NZ-1): cuFFT D2Z / Z2D 3-D, eigenvalue
 //    mu = kx^2 + ky^2 + (4/dz^2) sin^2(kz dz/2) (poisson.cu:174), persistent
 //    scratch instead of 3 cudaMalloc + 3 cudaFree per call (poisson.cu:77-102).
@@ -36,6 +37,7 @@
 
 namespace {
 
+#ifdef EK_XCHECK
 // ------------------------------ path 1 kernels ------------------------------
 // odd_extension (poisson.cu:114-158) on a real array; dq = c+ - c-
 __global__ void k_pack_odd(EkConst c, int NE, const double *__restrict__ dq, double *__restrict__ ext, double eps)
@@ -90,6 +92,7 @@ __global__ void k_unpack(EkConst c, const double *__restrict__ ext, double size,
     else v = ext[((size_t)z * c.NY + y) * c.NX + x] / size;
     phi[(size_t)z * c.plane + y * c.PX + x] = v;
 }
+#endif  // EK_XCHECK
 
 // ------------------------------ path 0 kernels ------------------------------
 // LU factor of the z-operator of every (kx,ky) column, once per handle:
@@ -218,6 +221,7 @@ __global__ void k_efield(EkConst c, const double *__restrict__ phi, double *ex, 
     ez[i] = 0.5 * (phi[(size_t)(zc - 1) * c.plane + y * c.PX + x] - phi[(size_t)(zc + 1) * c.plane + y * c.PX + x]) / c.dz;
 }
 
+#ifdef EK_XCHECK
 ek_status create_path1(ek_handle *h, EkPoisson &P, cudaStream_t st)
 {
     if (P.plans) return EK_OK;
@@ -233,6 +237,7 @@ ek_status create_path1(ek_handle *h, EkPoisson &P, cudaStream_t st)
     EK_CUFFT(h, cufftSetStream(P.plan_inv, st));
     return EK_OK;
 }
+#endif  // EK_XCHECK
 
 ek_status create_path0(ek_handle *h, EkPoisson &P, const ek_params &p, cudaStream_t st)
 {
@@ -374,6 +379,11 @@ ek_status ek_poisson_solve(ek_handle *h, EkPoisson &P, const ek_params &p, const
             n = 2;
         }
     } else {
+#ifndef EK_XCHECK
+        ek_set_error(h, "Poisson path 1 / EK_DC_LITERAL (the reference's odd-extension transform) is only in the "
+                        "cross-check build libek_b200_xcheck.so");
+        return EK_ERR_INVALID;
+#else
         ek_status s1 = create_path1(h, P, st);
         if (s1 != EK_OK) return s1;
         dim3 ge((c.NX + 127) / 128, c.NY, P.NE), gs((P.NXH + 127) / 128, c.NY, P.NE), gz((c.NX + 127) / 128, c.NY, c.NZ);
@@ -385,6 +395,7 @@ ek_status ek_poisson_solve(ek_handle *h, EkPoisson &P, const ek_params &p, const
         k_unpack<<<gz, b, 0, st>>>(c, P.real_ext, size, phi);
         h->phi_walls_dirty = false;
         n = 3;
+#endif
     }
     if (Ex) { ek_launch_efield(c, phi, Ex, Ey, Ez, st); ++n; }
     if (launches) *launches += n;

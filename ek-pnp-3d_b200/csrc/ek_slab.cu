@@ -90,6 +90,7 @@ ek_status ek_set_stream(ek_handle *h, void *stream)
     if (h->own_stream) cudaStreamDestroy(h->stream);
     h->stream = (cudaStream_t)stream;
     h->own_stream = false;
+    h->epoch += 1;
     if (h->poisson.plans) { cufftSetStream(h->poisson.plan_fwd, h->stream); cufftSetStream(h->poisson.plan_inv, h->stream); }
     if (h->poisson.plans2) { cufftSetStream(h->poisson.plan2_fwd, h->stream); cufftSetStream(h->poisson.plan2_inv, h->stream); }
     return EK_OK;

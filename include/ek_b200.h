@@ -147,9 +147,13 @@ ek_status ek_get_populations(ek_handle *h, int set, double *dst, int dst_on_devi
 ek_status ek_set_poisson_dc(ek_handle *h, int mode, double ghat0);
 
 /* options: "stream_mode" (EK_STREAM_*; before ek_init*), "zchunk",
- * "poisson_path" (0: 2-D FFT + tridiagonal z-solve, default; 1: the
- * reference's odd-extension 3-D FFT), "profile" (1: time every LBM/Poisson
- * launch with CUDA events). */
+ * "profile" (1: time every LBM/Poisson launch with CUDA events),
+ * "graph" (ek_step replays a CUDA graph of two coupled steps: 1 on, 0 off,
+ * -1 automatic = grids below 4 M cells, which are launch-latency bound),
+ * "kernel" (0 default; 3: general node path everywhere).
+ * Cross-check build only (libek_b200_xcheck.so, ek_is_xcheck_build()):
+ * "poisson_path" 1 = the reference's odd-extension 3-D FFT (poisson.cu:75-103
+ * literally), "kernel" 1/2 = eight-/five-warp LBM kernels, EK_DC_LITERAL. */
 ek_status ek_set_option(ek_handle *h, const char *key, long long value);
 /* counters: "steps", "zchunk", "lbm_launches", "poisson_launches", "kernel_launches";
  * times (ms, profile on): "lbm_ms", "poisson_ms" */
@@ -160,6 +164,7 @@ ek_status ek_reset_counters(ek_handle *h);
 void *ek_stream(ek_handle *h);
 const char *ek_last_error(ek_handle *h);
 int ek_abi_version(void);
+int ek_is_xcheck_build(void);   /* 1 in libek_b200_xcheck.so (test-only kernel variants + Poisson path 1), 0 in the product */
 int ek_device_count(void);   /* CUDA devices visible to the process (0: none -- there is no CPU path) */
 
 /* Diagnostics on device.  Replace current() (LBM.cu:2674-2710) and the

@@ -25,6 +25,11 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"{n} declared in ek_b200.h but not exported by libek_b200.so"
     assert L.ek_abi_version() == 1
+    assert L.ek_is_xcheck_build() == 0
+    X = ek.load_library(ek.XCHECK_LIB_PATH)       # the cross-check build exports the same ABI
+    for n in names:
+        assert hasattr(X, n), n
+    assert X.ek_is_xcheck_build() == 1
 
 
 def test_params_struct_matches_the_oracle_layout():

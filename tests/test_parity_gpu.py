@@ -195,7 +195,7 @@ def test_literal_dc_mode_is_a_constant_interior_shift(ek):
     init = synthetic_init(over)
     phis = {}
     for mode in (ek.DC_ZERO, ek.DC_LITERAL):
-        sim = ek.Simulation(ek.default_params(**over))
+        sim = ek.Simulation(ek.default_params(**over), xcheck=True)   # the literal transform is cross-check only
         sim.set_fields(init)
         sim.init_equilibrium()
         sim.set_poisson_dc(mode)
@@ -221,6 +221,48 @@ def test_startup_matches_the_oracle(ek):
         a, b = sim.populations(s), o.populations(s)
         assert np.abs(a - b).max() <= 1e-14 * np.abs(b).max()
     sim.close()
+
+
+def test_product_library_has_no_cross_check_variants(ek):
+    """libek_b200.so ships the hot path only: the slower kernel variants and the literal
+    odd-extension transform live in libek_b200_xcheck.so (test infrastructure)"""
+    assert ek.load_library().ek_is_xcheck_build() == 0
+    assert ek.load_library(ek.XCHECK_LIB_PATH).ek_is_xcheck_build() == 1
+    sim = ek.Simulation(ek.default_params(NX=8, NY=2, NZ=7))
+    for key, value in (("kernel", 1), ("kernel", 2), ("poisson_path", 1)):
+        with pytest.raises(ek.EkError):
+            sim.set_option(key, value)
+    with pytest.raises(ek.EkError):
+        sim.set_poisson_dc(ek.DC_LITERAL)
+    sim.set_option("kernel", 3)
+    sim.close()
+
+
+def test_step_graph_is_bitwise_identical(ek):
+    """ek_step replays a CUDA graph of two coupled steps on small grids (option "graph"): same
+    kernels, same arguments, so the same bits as the launch-by-launch loop"""
+    over = dict(NX=40, NY=5, NZ=21, uw=1.0e-4, exf=1.0e6)
+    init = synthetic_init(over)
+    res = {}
+    for mode in (ek.STREAM_AA, ek.STREAM_PUSH):
+        for graph in (0, 1, -1):
+            sim = ek.Simulation(ek.default_params(**over), stream_mode=mode)
+            sim.set_option("graph", graph)
+            sim.set_fields(init)
+            sim.init_equilibrium()
+            sim.step(11)
+            sim.step(1)
+            sim.step(8)
+            replays = sim.counter("graph_replays")
+            assert (replays == 0) if graph == 0 else (replays >= 6), (graph, replays)
+            assert sim.counter("steps") == 20
+            res[mode, graph] = (sim.fields(), np.stack([sim.populations(s) for s in range(4)]))
+            sim.close()
+    base_f, base_p = res[ek.STREAM_AA, 0]
+    for key, (f, p) in res.items():
+        for k in util.FIELDS:
+            assert np.array_equal(f[k], base_f[k]), (key, k)
+        assert np.array_equal(p, base_p), key
 
 
 def test_state_machine_errors(ek):
@@ -424,7 +466,7 @@ def test_poisson_paths_agree(ek, over):
     want = o.fields()
     got = {}
     for path in (0, 1):
-        sim = ek.Simulation(ek.default_params(**over))
+        sim = ek.Simulation(ek.default_params(**over), xcheck=(path == 1))   # path 0 = the product library
         sim.set_option("poisson_path", path)
         sim.set_fields(init)
         sim.init_equilibrium()
@@ -443,7 +485,7 @@ def test_prescribed_dc_is_the_same_shift_on_both_paths(ek):
     init = synthetic_init(over)
     res = {}
     for path in (0, 1):
-        sim = ek.Simulation(ek.default_params(**over))
+        sim = ek.Simulation(ek.default_params(**over), xcheck=(path == 1))
         sim.set_option("poisson_path", path)
         sim.set_fields(init)
         sim.init_equilibrium()
@@ -510,7 +552,7 @@ def test_kernel_variants_agree(ek):
     res = {}
     for kernel in (0, 1, 2, 3):
         for mode in (ek.STREAM_AA, ek.STREAM_PUSH):
-            sim = ek.Simulation(ek.default_params(**over), stream_mode=mode, zchunk=6)
+            sim = ek.Simulation(ek.default_params(**over), stream_mode=mode, zchunk=6, xcheck=kernel in (1, 2))
             sim.set_option("kernel", kernel)
             sim.set_fields(init)
             sim.init_equilibrium()
