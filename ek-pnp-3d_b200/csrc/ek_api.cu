@@ -305,7 +305,9 @@ ek_status ek_set_option(ek_handle *h, const char *key, long long value)
     if (!strcmp(key, "kernel")) {
         // 0: four warps, lean deep-interior path (default); 1: eight warps; 2: five warps;
         // 3: four warps, general path everywhere (cross-check of the lean path)
-        if (value < 0 || value > 3) return EK_ERR_INVALID;
+        // 5: x-marching rows with sector-aligned stores for the odd A-A step (measured slower than the
+        // z-walking default; kept selectable for the A/B profile)
+        if (value < 0 || value > 5 || value == 4) return EK_ERR_INVALID;
 #ifndef EK_XCHECK
         if (value == 1 || value == 2) { ek_set_error(h, "kernel variants 1/2 are only in the cross-check build libek_b200_xcheck.so"); return EK_ERR_INVALID; }
 #endif
@@ -495,6 +497,12 @@ ek_status ek_stream_collide_save_range(ek_handle *h, int write_fields, int zbloc
     else if (h->kernel == 2) EK_CUDA(h, ek_launch_step5(a, mode, write_fields != 0, h->e_from_arrays, h->stream));
     else
 #endif
+    if (mode == EK_MODE_AA_ODD && h->kernel == 5 && !h->e_from_arrays && ek_march_applicable(h->c)) {
+        // odd step: x-marching rows with sector-aligned stores (ek_lbm.cu)
+        const int z0 = zblock0 * h->zchunk;
+        const int z1 = zblock1 > 0 ? (zblock1 * h->zchunk < h->c.NZ ? zblock1 * h->zchunk : h->c.NZ) : h->c.NZ;
+        EK_CUDA(h, ek_launch_march(a, write_fields != 0, z0, z1, h->stream));
+    } else
     EK_CUDA(h, ek_launch_step(a, mode, write_fields != 0, h->e_from_arrays, h->kernel != 3, h->stream));
     if (h->profile) {
         EK_CUDA(h, cudaEventRecord(e1, h->stream));
@@ -554,8 +562,9 @@ static bool graph_usable(ek_handle *h)
     // the legacy default stream of the shim cannot be captured)
     const bool path1 = h->poisson_path == 1 || h->dc_mode == EK_DC_LITERAL;
     return want && !h->profile && h->dc_mode != EK_DC_PRESCRIBED && !h->e_from_arrays && !h->phi_walls_dirty &&
-           !h->slab && (path1 ? h->poisson.plans : h->poisson.plans2) &&
-           (h->stream_mode == EK_STREAM_PUSH || h->parity == 0) && h->stream != nullptr;
+           !h->slab && (path1 ? h->poisson.plans : h->poisson.plans2) && h->stream != nullptr &&
+           // the pair was captured from the natural layout (A-A parity 0 / push lattice 0): replay from there only
+           h->parity == 0 && h->cur == 0;
 }
 
 // capture two steps on the handle's stream (nothing executes), instantiate

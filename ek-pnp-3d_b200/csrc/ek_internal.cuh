@@ -102,6 +102,10 @@ struct StepArgs {
     double *fld[7];       // rho ux uy uz charge chargen T (only when fields are written)
     int zchunk;
     int zblock0, nzblocks;  // sub-range of z-chunks for this launch (nzblocks = 0: all)
+    // x-marching launch of the odd A-A step (ek_march_kernel): deep-interior planes [march_z0, march_z0 +
+    // march_planes) walk their x-rows; the wall-adjacent plane ranges take the general node path
+    int march_z0, march_planes;
+    int wall_n, wall_z0[2], wall_z1[2];
 };
 
 // ---------------------------------------------------------------------------
@@ -191,6 +195,9 @@ void ek_slab_poisson_destroy(ek_handle *h);
 // ---------------------------------------------------------------------------
 cudaError_t ek_launch_step(const StepArgs &a, int mode, bool write_fields, bool e_from_arrays, bool lean,
                            cudaStream_t st);
+// odd A-A step with sector-aligned stores (x-marching warps); planes [z0, z1) of the launch
+cudaError_t ek_launch_march(StepArgs a, bool write_fields, int z0, int z1, cudaStream_t st);
+bool ek_march_applicable(const EkConst &c);
 cudaError_t ek_launch_step5(const StepArgs &a, int mode, bool write_fields, bool e_from_arrays, cudaStream_t st);
 cudaError_t ek_launch_step8(const StepArgs &a, int mode, bool write_fields, bool e_from_arrays, cudaStream_t st);
 cudaError_t ek_launch_export(const StepArgs &a, int mode, int set, double *dst, cudaStream_t st);

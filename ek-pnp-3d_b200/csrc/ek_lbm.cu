@@ -26,6 +26,9 @@
 //  * a CTA walks a chunk of z so that the thread that owns the z = 0 node also
 //    owns z = 1: the bottom wall takes minus the z = 1 momentum (LBM.cu:663-801)
 //    and in an in-place scheme only the owner may read that node.
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "ek_lbm_common.cuh"
 
 namespace {
@@ -47,6 +50,24 @@ template <int NT> __device__ __forceinline__ void bar_velocity() { asm volatile(
 // ---------------------------------------------------------------------------
 // scalar roles: cation (s = 1), anion (s = 2), temperature (s = 3)
 // ---------------------------------------------------------------------------
+// TRT relaxation of the opposite pair (d, d+1) of a scalar set (LBM.cu:1148-1845): shared by every
+// node path, so that all of them produce the same bits
+template <int d>
+__device__ __forceinline__ void scalar_pair_trt(const double S[27], const double wcm[4], double omusq, double vtx,
+                                                double vty, double vtz, double wp, double wmn, double &Oa, double &Ob)
+{
+    constexpr int o = d + 1, cls = ek_wclass(d);
+    const double s_ = cdot<d>(vtx, vty, vtz);
+    const double wm_ = wcm[cls];
+    const double ep = wm_ * (omusq + 0.5 * s_ * s_);
+    const double em = wm_ * s_;
+    const double a = S[d], b = S[o];
+    const double np_ = wp * (0.5 * (a + b) - ep);
+    const double nm_ = wmn * (0.5 * (a - b) - em);
+    Oa = a - (np_ + nm_);
+    Ob = b - (np_ - nm_);
+}
+
 template <int MODE, bool LEAN, int p>
 struct ScalarPairs {
     // TRT relaxation of the opposite pair (d, d+1), d = 2p+1 (LBM.cu:1148-1845),
@@ -57,15 +78,8 @@ struct ScalarPairs {
                                                double *Wn, bool act)
     {
         constexpr int d = 2 * p + 1, o = d + 1, cls = ek_wclass(d);
-        const double s_ = cdot<d>(vtx, vty, vtz);
-        const double wm_ = wcm[cls];
-        const double ep = wm_ * (omusq + 0.5 * s_ * s_);
-        const double em = wm_ * s_;
-        const double a = S[d], b = S[o];
-        const double np_ = wp * (0.5 * (a + b) - ep);
-        const double nm_ = wmn * (0.5 * (a - b) - em);
-        const double Oa = a - (np_ + nm_);
-        const double Ob = b - (np_ - nm_);
+        double Oa, Ob;
+        scalar_pair_trt<d>(S, wcm, omusq, vtx, vty, vtz, wp, wmn, Oa, Ob);
         if (act) {
             if (LEAN) {
                 putx<MODE, d, true>(lout, nb, la, Oa);
@@ -219,6 +233,29 @@ __device__ __forceinline__ void scalar_role(const StepArgs &a, Sh &sh, const int
 // ---------------------------------------------------------------------------
 // fluid role
 // ---------------------------------------------------------------------------
+// TRT + Guo forcing of the opposite pair (d, d+1) of the fluid set, interior nodes
+template <int d>
+__device__ __forceinline__ void fluid_pair_trt(const double S[27], const double wcr[4], double omusq, const double u[3],
+                                               const double F[3], double uF, const EkConst &c, double &Oa, double &Ob)
+{
+    constexpr int o = d + 1, cls = ek_wclass(d);
+    const double cu = cdot<d>(u[0], u[1], u[2]);
+    const double cF = cdot<d>(F[0], F[1], F[2]);
+    const double s_ = cu * c.tfac;
+    const double wr = wcr[cls];
+    const double ep = wr * (omusq + 0.5 * s_ * s_);
+    const double em = wr * s_;
+    const double a = S[d], b = S[o];
+    const double np_ = c.wp[0] * (0.5 * (a + b) - ep);
+    const double nm_ = c.wm[0] * (0.5 * (a - b) - em);
+    // Guo forcing split into its symmetric / antisymmetric parts
+    // (LBM.cu:1107-1145, 1608-1689): F+ = coe*((c.u)(c.F)*cflinv2 - u.F), F- = coe*cflinv*(c.F)
+    const double Fp = c.sp * (c.coe[cls] * (cu * cF * c.cflinv2 - uF));
+    const double Fm = c.sm * (c.coe[cls] * c.cflinv * cF);
+    Oa = a - (np_ + nm_) + c.dt * (Fp + Fm);
+    Ob = b - (np_ - nm_) + c.dt * (Fp - Fm);
+}
+
 template <int MODE, bool LEAN, int p>
 struct FluidPairs {
     static __device__ __forceinline__ void run(const double S[27], double wcr[4], double omusq, const double u[3],
@@ -228,21 +265,7 @@ struct FluidPairs {
         constexpr int d = 2 * p + 1, o = d + 1, cls = ek_wclass(d);
         double Oa, Ob;
         if (LEAN || !wall) {
-            const double cu = cdot<d>(u[0], u[1], u[2]);
-            const double cF = cdot<d>(F[0], F[1], F[2]);
-            const double s_ = cu * c.tfac;
-            const double wr = wcr[cls];
-            const double ep = wr * (omusq + 0.5 * s_ * s_);
-            const double em = wr * s_;
-            const double a = S[d], b = S[o];
-            const double np_ = c.wp[0] * (0.5 * (a + b) - ep);
-            const double nm_ = c.wm[0] * (0.5 * (a - b) - em);
-            // Guo forcing split into its symmetric / antisymmetric parts
-            // (LBM.cu:1107-1145, 1608-1689): F+ = coe*((c.u)(c.F)*cflinv2 - u.F), F- = coe*cflinv*(c.F)
-            const double Fp = c.sp * (c.coe[cls] * (cu * cF * c.cflinv2 - uF));
-            const double Fm = c.sm * (c.coe[cls] * c.cflinv * cF);
-            Oa = a - (np_ + nm_) + c.dt * (Fp + Fm);
-            Ob = b - (np_ - nm_) + c.dt * (Fp - Fm);
+            fluid_pair_trt<d>(S, wcr, omusq, u, F, uF, c, Oa, Ob);
         } else {
             // full-way bounce-back from the PRE-collision populations
             // (LBM.cu:1862-1887), moving-wall terms at the top (LBM.cu:1902-1927)
@@ -605,6 +628,276 @@ cudaError_t launch_mode5(const StepArgs &a, bool full, bool earr, dim3 grid, cud
 }
 #endif  // EK_XCHECK
 
+// ---------------------------------------------------------------------------
+// x-marching variant of the ODD A-A step for the deep-interior planes.
+//
+// In the odd step a node writes slot d at x + c_d: for the 18 directions with c_x = +-1 a warp's
+// 256-byte store starts 8 bytes off a sector boundary and its last element lands in the NEXT x-tile
+// (6912 bytes away): 9 sectors, two of them partial, per request.  Measured at 256^3 (DESIGN.md
+// 3.6): 0.31 ms of the 5.28 ms launch, the largest single loss against the even step.
+//
+// Here a CTA (still one warp per population set) owns one (y, z) ROW and walks its x-tiles:
+//   * c_x = +1 outputs: lane i's value belongs to column i+1 -> one shuffle up; lane 0 takes what
+//     lane 31 produced for the previous tile (9 doubles per warp carried through shared memory);
+//     the store is then the full aligned 256-byte segment of tile T.
+//   * c_x = -1 outputs: lane i's value belongs to column i-1 and column 31 of tile T comes from lane 0
+//     of tile T+1 -> the warp parks the 9 values in a two-tile ring in shared memory and writes
+//     tile T-1 as full aligned segments one iteration later.
+// Only the two ends of a row (periodic wrap, or the ghost columns of an x-slab) remain single-element
+// stores: 2 per row and direction instead of 2 per tile.  The loads keep the neighbour gather of the
+// lean path.  Same arithmetic (scalar_pair_trt / fluid_pair_trt), same bits; requires NX % 32 == 0.
+// ---------------------------------------------------------------------------
+struct MarchSm {                 // per warp
+    double ring[9][64];          // c_x = -1 outputs of the tiles T-1 / T (halves alternate)
+    double carry[2][9];          // lane 31's c_x = +1 outputs of tile T (index T & 1)
+};
+
+// index of direction d among the nine directions with the same c_x sign
+__host__ __device__ constexpr int ek_xrank(int d)
+{
+    int k = 0;
+    for (int e = 1; e < d; ++e)
+        if (ek_cx(e) == ek_cx(d)) ++k;
+    return k;
+}
+
+struct MarchCtx {
+    LeanAddr la;
+    unsigned ly[3];              // lattice offsets of the rows y-1, y, y+1 within a plane
+    int lane, T, NT;
+    MarchSm *ms;
+};
+
+__device__ __forceinline__ void march_tile(MarchCtx &m, const EkConst &c, int y)
+{
+    // neighbour columns of x = 32 T + lane; the row ends wrap (or reach the ghost columns of a slab)
+    const int x = m.T * 32 + m.lane;
+    const unsigned ox1 = (unsigned)m.T * EK_TILE_ELEMS + (unsigned)m.lane;
+    const unsigned ox0 = m.lane > 0 ? ox1 - 1u : (m.T > 0 ? ox1 - (unsigned)(EK_TILE_ELEMS - 31) : ek_lat_col(c.xlo));
+    const unsigned ox2 = m.lane < 31 ? ox1 + 1u : (m.T < m.NT - 1 ? ox1 + (unsigned)(EK_TILE_ELEMS - 31) : ek_lat_col(c.xhi));
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        m.la.oxy[j][0] = m.ly[j] + ox0;
+        m.la.oxy[j][1] = m.ly[j] + ox1;
+        m.la.oxy[j][2] = m.ly[j] + ox2;
+    }
+    const int ym = y == 0 ? c.NY - 1 : y - 1, yp = y == c.NY - 1 ? 0 : y + 1;
+    m.la.fc = y * c.PX + x;
+    m.la.fxm = y * c.PX + (x == 0 ? c.xlo : x - 1);
+    m.la.fxp = y * c.PX + (x == c.NX - 1 ? c.xhi : x + 1);
+    m.la.fym = ym * c.PX + x;
+    m.la.fyp = yp * c.PX + x;
+    m.la.fdq = (long long)y * c.dq_sy + x;
+}
+
+// deliver the post-collision value of direction d (odd A-A step: slot d of the node at x + c_d)
+template <int d>
+__device__ __forceinline__ void march_put(const MarchCtx &m, double v)
+{
+    double *row = m.la.b[1 + ek_cz(d)];
+    if (ek_cx(d) == 0) {
+        EK_ST(row + m.la.oxy[1 + ek_cy(d)][1] + d * EK_TILE, v);
+    } else if (ek_cx(d) > 0) {
+        constexpr int k = ek_xrank(d);
+        double w = __shfl_up_sync(0xffffffffu, v, 1);
+        if (m.lane == 31) {
+            m.ms->carry[m.T & 1][k] = v;
+            if (m.T == m.NT - 1) EK_ST(row + m.la.oxy[1 + ek_cy(d)][2] + d * EK_TILE, v);   // end of the row: column xhi
+        }
+        if (m.lane == 0 && m.T > 0) w = m.ms->carry[(m.T & 1) ^ 1][k];
+        if (m.lane > 0 || m.T > 0) EK_ST(row + m.la.oxy[1 + ek_cy(d)][1] + d * EK_TILE, w);
+    } else {
+        constexpr int k = ek_xrank(d);
+        m.ms->ring[k][(m.T & 1) * 32 + m.lane] = v;
+        if (m.lane == 0 && m.T == 0) EK_ST(row + m.la.oxy[1 + ek_cy(d)][0] + d * EK_TILE, v);   // start of the row: column xlo
+    }
+}
+
+// write the parked c_x = -1 outputs of tile `T - 1` (all 32 columns), or -- last = true, after the
+// loop -- of the final tile (columns 0..30; column 31 was written by the first iteration / is a ghost)
+template <int d>
+struct MarchDrain {
+    static __device__ __forceinline__ void run(const MarchCtx &m, bool last)
+    {
+        if (ek_cx(d) < 0) {
+            constexpr int k = ek_xrank(d);
+            const int half = last ? (m.T & 1) : ((m.T & 1) ^ 1);
+            const double w = m.ms->ring[k][(half * 32 + m.lane + 1) & 63];
+            double *q = m.la.b[1 + ek_cz(d)] + m.la.oxy[1 + ek_cy(d)][1] + d * EK_TILE;
+            if (!last) EK_ST(q - EK_TILE_ELEMS, w);
+            else if (m.lane < 31) EK_ST(q, w);
+        }
+        MarchDrain<d + 1>::run(m, last);
+    }
+};
+template <>
+struct MarchDrain<27> {
+    static __device__ __forceinline__ void run(const MarchCtx &, bool) {}
+};
+
+template <int p>
+struct MarchScalarPairs {
+    static __device__ __forceinline__ void run(const double S[27], const double wcm[4], double omusq, double vtx, double vty,
+                                               double vtz, double wp, double wmn, const MarchCtx &m)
+    {
+        constexpr int d = 2 * p + 1, o = d + 1;
+        double Oa, Ob;
+        scalar_pair_trt<d>(S, wcm, omusq, vtx, vty, vtz, wp, wmn, Oa, Ob);
+        march_put<d>(m, Oa);
+        march_put<o>(m, Ob);
+        MarchScalarPairs<p + 1>::run(S, wcm, omusq, vtx, vty, vtz, wp, wmn, m);
+    }
+};
+template <>
+struct MarchScalarPairs<13> {
+    static __device__ __forceinline__ void run(const double *, const double *, double, double, double, double, double,
+                                               double, const MarchCtx &) {}
+};
+
+template <int p>
+struct MarchFluidPairs {
+    static __device__ __forceinline__ void run(const double S[27], const double wcr[4], double omusq, const double u[3],
+                                               const double F[3], double uF, const EkConst &c, const MarchCtx &m)
+    {
+        constexpr int d = 2 * p + 1, o = d + 1;
+        double Oa, Ob;
+        fluid_pair_trt<d>(S, wcr, omusq, u, F, uF, c, Oa, Ob);
+        march_put<d>(m, Oa);
+        march_put<o>(m, Ob);
+        MarchFluidPairs<p + 1>::run(S, wcr, omusq, u, F, uF, c, m);
+    }
+};
+template <>
+struct MarchFluidPairs<13> {
+    static __device__ __forceinline__ void run(const double *, const double *, double, const double *, const double *,
+                                               double, const EkConst &, const MarchCtx &) {}
+};
+
+__device__ __forceinline__ void march_begin(MarchCtx &m, const EkConst &c, double *lat, MarchSm *ms, int lane, int y, int z)
+{
+    m.lane = lane;
+    m.NT = c.NX >> 5;
+    m.ms = ms;
+    const int ym = y == 0 ? c.NY - 1 : y - 1, yp = y == c.NY - 1 ? 0 : y + 1;
+    m.ly[0] = (unsigned)ym * c.lrow; m.ly[1] = (unsigned)y * c.lrow; m.ly[2] = (unsigned)yp * c.lrow;
+    lean_set_z(m.la, lat, c, z);
+}
+
+// the x-row (y, z) of a scalar set; the arithmetic is scalar_node<.., LEAN = true>
+template <bool FULL, int NT_>
+__device__ __forceinline__ void march_scalar_row(const StepArgs &a, Sh &sh, MarchSm *ms, const int s, const int lane,
+                                                 const int y, const int z)
+{
+    const EkConst &c = a.c;
+    const double wp = c.wp[s], wmn = c.wm[s];
+    const bool is_temp = (s == 3);
+    const double Ks = s == 1 ? c.K : c.Kn;
+    double *mom_sh = s == 1 ? sh.cp : (s == 2 ? sh.cn : sh.T);
+    MarchCtx m;
+    march_begin(m, c, a.in[s], ms, lane, y, z);
+    for (m.T = 0; m.T < m.NT; ++m.T) {
+        march_tile(m, c, y);
+        double S[27];
+        gather27_lean<EK_MODE_AA_ODD>(m.la, S);
+        const double mm = sum27(S);
+        double E[3] = {0.0, 0.0, 0.0};
+        mom_sh[lane] = mm;
+        if (is_temp) {
+            efield_lean(a, m.la, z, E);
+            sh.E[0][lane] = E[0]; sh.E[1][lane] = E[1]; sh.E[2][lane] = E[2];
+        }
+        if (FULL) a.fld[3 + s][(size_t)z * c.plane + m.la.fc] = mm;   // charge, chargen, T (LBM.cu:811-813)
+        bar_moments<NT_>();
+        if (!is_temp) { E[0] = sh.E[0][lane]; E[1] = sh.E[1][lane]; E[2] = sh.E[2][lane]; }
+        bar_velocity<NT_>();
+        double vx = sh.u[0][lane], vy = sh.u[1][lane], vz = sh.u[2][lane];
+        if (!is_temp) {
+            vx = vx + Ks * E[0];
+            vy = vy + Ks * E[1];
+            vz = vz + Ks * E[2];
+        }
+        double wcm[4] = {c.w[0] * mm, c.w[1] * mm, c.w[2] * mm, c.w[3] * mm};
+        const double omusq = 1.0 - 0.5 * (vx * vx + vy * vy + vz * vz) * c.inv_cs2;
+        const double vtx = vx * c.tfac, vty = vy * c.tfac, vtz = vz * c.tfac;
+        const double O0 = S[0] - wp * (S[0] - wcm[0] * omusq);
+        lean_ptr(m.la.b[1], m.la.oxy[1][1])[0] = O0;
+        MarchScalarPairs<0>::run(S, wcm, omusq, vtx, vty, vtz, wp, wmn, m);
+        __syncwarp();
+        if (m.T > 0) MarchDrain<1>::run(m, false);
+    }
+    m.T = m.NT - 1;
+    MarchDrain<1>::run(m, true);
+}
+
+// the x-row (y, z) of the fluid set; the arithmetic is fluid_node<.., LEAN = true>
+template <bool FULL, int NT_>
+__device__ __forceinline__ void march_fluid_row(const StepArgs &a, Sh &sh, MarchSm *ms, const int lane, const int y,
+                                                const int z)
+{
+    const EkConst &c = a.c;
+    MarchCtx m;
+    march_begin(m, c, a.in[0], ms, lane, y, z);
+    for (m.T = 0; m.T < m.NT; ++m.T) {
+        march_tile(m, c, y);
+        double S[27];
+        gather27_lean<EK_MODE_AA_ODD>(m.la, S);
+        const double rho = sum27(S);
+        double mo[3];
+        momentum(S, mo);
+        const double rhoinv = 1.0 / rho;
+        bar_moments<NT_>();
+        const double E[3] = {sh.E[0][lane], sh.E[1][lane], sh.E[2][lane]};
+        const double dq = sh.cp[lane] - sh.cn[lane];
+        double F[3], ex_[3], u[3];
+        node_force_and_momentum(c, mo, dq, sh.T[lane], E, F, ex_);
+        u[0] = rhoinv * ex_[0]; u[1] = rhoinv * ex_[1]; u[2] = rhoinv * ex_[2];
+        sh.u[0][lane] = u[0]; sh.u[1][lane] = u[1]; sh.u[2][lane] = u[2];
+        bar_velocity<NT_>();
+        {
+            const size_t i = (size_t)z * c.plane + m.la.fc;
+            a.dq[(size_t)z * c.dq_sz + m.la.fdq] = dq;
+            if (FULL) {  // LBM.cu:807-810
+                a.fld[0][i] = rho; a.fld[1][i] = u[0]; a.fld[2][i] = u[1]; a.fld[3][i] = u[2];
+            }
+        }
+        double wcr[4] = {c.w[0] * rho, c.w[1] * rho, c.w[2] * rho, c.w[3] * rho};
+        const double omusq = 1.0 - 0.5 * (u[0] * u[0] + u[1] * u[1] + u[2] * u[2]) * c.inv_cs2;
+        const double uF = u[0] * F[0] + u[1] * F[1] + u[2] * F[2];
+        const double O0 = S[0] - c.wp[0] * (S[0] - wcr[0] * omusq) + c.dt * (c.sp * (-c.coe[0] * uF));
+        lean_ptr(m.la.b[1], m.la.oxy[1][1])[0] = O0;
+        MarchFluidPairs<0>::run(S, wcr, omusq, u, F, uF, c, m);
+        __syncwarp();
+        if (m.T > 0) MarchDrain<1>::run(m, false);
+    }
+    m.T = m.NT - 1;
+    MarchDrain<1>::run(m, true);
+}
+
+template <bool FULL>
+__global__ void __launch_bounds__(128, EK_MIN_CTAS) ek_march_kernel(const __grid_constant__ StepArgs a)
+{
+    __shared__ Sh sh;
+    __shared__ MarchSm msm[4];
+    const EkConst &c = a.c;
+    const int lane = threadIdx.x & 31;
+    const int role = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int y = blockIdx.x;
+    if ((int)blockIdx.y < a.march_planes) {
+        const int z = a.march_z0 + blockIdx.y;
+        if (role == 0) march_fluid_row<FULL, 128>(a, sh, &msm[0], lane, y, z);
+        else march_scalar_row<FULL, 128>(a, sh, &msm[role], role, lane, y, z);
+    } else {
+        // wall-adjacent planes (z = 0, 1 and NZ-2, NZ-1): the general node path, one x-tile per CTA
+        const int w = blockIdx.y - a.march_planes, NT = c.NX >> 5;
+        const int side = w / NT, tile = w - side * NT;
+        const int x = tile * 32 + lane;
+        const int z0 = a.wall_z0[side], z1 = a.wall_z1[side];
+        const int pi = y * c.PX + x;
+        if (role == 0) fluid_role<EK_MODE_AA_ODD, FULL, 128, false>(a, sh, lane, true, x, y, z0, z1);
+        else scalar_role<EK_MODE_AA_ODD, FULL, false, 128, false>(a, sh, role, lane, true, x, y, pi, z0, z1);
+    }
+}
+
 template <int MODE>
 cudaError_t launch_mode(const StepArgs &a, bool full, bool earr, bool lean, dim3 grid, cudaStream_t st)
 {
@@ -633,6 +926,43 @@ cudaError_t ek_launch_step(const StepArgs &a, int mode, bool write_fields, bool 
     case EK_MODE_AA_ODD: return launch_mode<EK_MODE_AA_ODD>(a, write_fields, e_from_arrays, lean, grid, st);
     default: return launch_mode<EK_MODE_PUSH>(a, write_fields, e_from_arrays, false, grid, st);
     }
+}
+
+bool ek_march_applicable(const EkConst &c) { return (c.NX % 32) == 0 && c.NZ >= 6; }
+
+// odd A-A step of the planes [z0, z1): x-marching rows for the deep interior (2 <= z <= NZ-3), the general
+// node path for the wall-adjacent planes, in ONE launch
+cudaError_t ek_launch_march(StepArgs a, bool write_fields, int z0, int z1, cudaStream_t st)
+{
+    const EkConst &c = a.c;
+    const int m0 = z0 > 2 ? z0 : 2, m1 = z1 < c.NZ - 2 ? z1 : c.NZ - 2;
+    a.march_z0 = m0;
+    a.march_planes = m1 > m0 ? m1 - m0 : 0;
+    a.wall_n = 0;
+    if (z0 < 2) { a.wall_z0[a.wall_n] = z0; a.wall_z1[a.wall_n] = z1 < 2 ? z1 : 2; ++a.wall_n; }
+    if (z1 > c.NZ - 2) { a.wall_z0[a.wall_n] = z0 > c.NZ - 2 ? z0 : c.NZ - 2; a.wall_z1[a.wall_n] = z1; ++a.wall_n; }
+    dim3 grid(c.NY, a.march_planes + a.wall_n * (c.NX / 32));
+    if (grid.y == 0) return cudaSuccess;
+    // 21 KB of static shared memory per CTA: ask for a carve-out that keeps four CTAs per SM resident
+    // (the default heuristic may pick a smaller one and the kernel loses a quarter of its warps)
+    static bool configured = false;
+    if (!configured) {
+        const char *env = getenv("EK_MARCH_CARVEOUT");
+        const int pct = env ? atoi(env) : 50;
+        if (pct >= 0) {
+            cudaFuncSetAttribute(ek_march_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            cudaFuncSetAttribute(ek_march_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        }
+        if (getenv("EK_DEBUG")) {
+            int nb = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ek_march_kernel<false>, 128, 0);
+            fprintf(stderr, "ek_march_kernel: %d CTAs per SM (carve-out %d %%)\n", nb, pct);
+        }
+        configured = true;
+    }
+    if (write_fields) ek_march_kernel<true><<<grid, 128, 0, st>>>(a);
+    else ek_march_kernel<false><<<grid, 128, 0, st>>>(a);
+    return cudaGetLastError();
 }
 
 #ifdef EK_XCHECK

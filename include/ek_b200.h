@@ -150,7 +150,8 @@ ek_status ek_set_poisson_dc(ek_handle *h, int mode, double ghat0);
  * "profile" (1: time every LBM/Poisson launch with CUDA events),
  * "graph" (ek_step replays a CUDA graph of two coupled steps: 1 on, 0 off,
  * -1 automatic = grids below 4 M cells, which are launch-latency bound),
- * "kernel" (0 default; 3: general node path everywhere).
+ * "kernel" (0 default: z-walking CTAs with the lean deep-interior node path; 3: general node
+ * path everywhere; 5: x-marching rows with sector-aligned stores for the odd A-A step).
  * Cross-check build only (libek_b200_xcheck.so, ek_is_xcheck_build()):
  * "poisson_path" 1 = the reference's odd-extension 3-D FFT (poisson.cu:75-103
  * literally), "kernel" 1/2 = eight-/five-warp LBM kernels, EK_DC_LITERAL. */
@@ -300,6 +301,37 @@ ek_status ek_multi_set_pipeline(ek_multi *m, int on);   /* 1: overlap streams (d
 int ek_multi_slabs(ek_multi *m);
 ek_handle *ek_multi_slab(ek_multi *m, int s);
 const char *ek_multi_last_error(ek_multi *m);
+
+/* ------------------------------------------------------------------------
+ * Multi-GPU with ONE PROCESS PER GPU (ek_rank.cu): the layout of torchrun / mpirun launchers
+ * and of bench.py --gpus N.  Every process owns one x-slab; halos travel as ncclSend/ncclRecv
+ * between ring neighbours, the Poisson transposes as grouped send/recv with all ranks, on side
+ * streams of the rank so that they overlap the LBM launches -- all of it driven from C++, no host
+ * language between the launches of a step.  NCCL is loaded at run time (libnccl.so.2).
+ * Rank 0 creates the id block and the launcher broadcasts it:
+ *     char id[ek_rank_nccl_id_bytes()];  if (rank == 0) ek_rank_nccl_unique_id(id);  <broadcast id>
+ *     ek_rank_create(&global, device, rank, nranks, id, 0, &r);          (collective)
+ *     ek_rank_init(r);  ek_rank_step(r, n);  ek_get_field(ek_rank_slab(r), ...)   -- this rank's columns
+ * Every ek_rank_init*, ek_rank_step* call is collective (same arguments on every rank).
+ * ------------------------------------------------------------------------ */
+typedef struct ek_rank ek_rank;
+int ek_rank_nccl_id_bytes(void);
+ek_status ek_rank_nccl_unique_id(void *id);
+int ek_rank_nccl_version(void);                          /* e.g. 22809; 0: libnccl could not be loaded */
+ek_status ek_rank_create(const ek_params *global, int device, int rank, int nranks, const void *nccl_id,
+                         int poisson_chunks, ek_rank **out);
+ek_status ek_rank_destroy(ek_rank *r);
+ek_handle *ek_rank_slab(ek_rank *r);                     /* this rank's slab: fields, options, counters */
+int ek_rank_chunks(ek_rank *r);
+ek_status ek_rank_set_pipeline(ek_rank *r, int overlap, int overlap_back);
+ek_status ek_rank_init_fields(ek_rank *r);               /* initialization(), LBM.cu:68-146 */
+ek_status ek_rank_init_equilibrium(ek_rank *r);          /* init_equilibrium(), LBM.cu:150-463 */
+ek_status ek_rank_init(ek_rank *r);
+ek_status ek_rank_step(ek_rank *r, int nsteps);          /* main.cu:189-200 */
+ek_status ek_rank_step_timed(ek_rank *r, int nsteps, float *ms);   /* this rank's device time; max over ranks = the job's */
+ek_status ek_rank_sync(ek_rank *r);
+ek_status ek_rank_get_counter(ek_rank *r, const char *key, double *value);   /* + "nccl_groups" */
+const char *ek_rank_last_error(ek_rank *r);
 
 #ifdef __cplusplus
 }

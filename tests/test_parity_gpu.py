@@ -543,24 +543,29 @@ def test_reference_signature_shim(ek):
     check(util.field_errors(got, want))
 
 
-def test_kernel_variants_agree(ek):
-    """four-, five- and eight-warp step kernels: 0 (lean deep-interior path), 3
-    (general path everywhere) and 2 chain the sums in the reference's order and
-    must agree bit for bit; 1 adds two partial sums."""
-    over = dict(NX=40, NY=5, NZ=21, uw=1.0e-4, exf=1.0e6)
+@pytest.mark.parametrize("NX", [40, 64, 96])
+def test_kernel_variants_agree(ek, NX):
+    """LBM kernel variants: 0 (default: z-walking CTAs, lean deep-interior path), 5 (x-marching rows
+    with sector-aligned stores for the odd A-A step when NX % 32 == 0), 3 (general node path
+    everywhere) and the cross-check build's five-warp kernel 2 chain the sums in the reference's
+    order and must agree bit for bit; the eight-warp kernel 1 adds two partial sums."""
+    over = dict(NX=NX, NY=5, NZ=21, uw=1.0e-4, exf=1.0e6)
     init = synthetic_init(over)
     res = {}
-    for kernel in (0, 1, 2, 3):
+    for kernel in (0, 1, 2, 3, 5):
         for mode in (ek.STREAM_AA, ek.STREAM_PUSH):
             sim = ek.Simulation(ek.default_params(**over), stream_mode=mode, zchunk=6, xcheck=kernel in (1, 2))
             sim.set_option("kernel", kernel)
+            sim.set_option("graph", 0)
             sim.set_fields(init)
             sim.init_equilibrium()
             sim.step(7)
             res[kernel, mode] = (sim.fields(), np.stack([sim.populations(s) for s in range(4)]))
             sim.close()
-    base_f, base_p = res[0, ek.STREAM_AA]
-    for key in ((0, ek.STREAM_PUSH), (2, ek.STREAM_AA), (2, ek.STREAM_PUSH), (3, ek.STREAM_AA), (3, ek.STREAM_PUSH)):
+    base_f, base_p = res[3, ek.STREAM_AA]
+    for key in res:
+        if key[0] == 1:
+            continue
         f, p = res[key]
         for k in util.FIELDS:
             assert np.array_equal(f[k], base_f[k]), (key, k)
@@ -570,6 +575,30 @@ def test_kernel_variants_agree(ek):
     want, _ = oracle_run(over, init, 7)
     for key in res:
         check(util.field_errors(res[key][0], want))
+
+
+def test_marching_odd_step_in_z_ranges_and_with_fields(ek):
+    """the x-marching odd step launched per z-block range (as the slab pipeline does) and with the
+    macroscopic arrays written on odd steps: bit-identical to the z-walking kernel"""
+    over = dict(NX=64, NY=6, NZ=23, exf=1.0e6)
+    init = synthetic_init(over)
+    res = []
+    for kernel in (0, 5):
+        sim = ek.Simulation(ek.default_params(**over), zchunk=4)
+        sim.set_option("kernel", kernel)
+        sim.set_fields(init)
+        sim.init_equilibrium()
+        nb = -(-23 // 4)
+        for step in range(6):
+            cuts = [0, 1, 3, nb] if kernel == 5 else [0, nb]
+            for b0, b1 in zip(cuts[:-1], cuts[1:]):
+                sim._ck(sim.L.ek_stream_collide_save_range(sim.h, 1, b0, b1, int(b1 == nb)), "range")
+            sim.fast_Poisson(True)
+        res.append((sim.fields(), np.stack([sim.populations(s) for s in range(4)])))
+        sim.close()
+    for k in util.FIELDS:
+        assert np.array_equal(res[0][0][k], res[1][0][k]), k
+    assert np.array_equal(res[0][1], res[1][1])
 
 
 # ---------------------------------------------------------------------------
