@@ -204,6 +204,143 @@ def run_reference(args, rank: int):
     print(json.dumps(line), flush=True)
 
 
+def _timed_ranks(rs, dist, torch, steps, warmup):
+    """W warm-up steps, then K steps bracketed by a barrier + synchronize on both sides; device time
+    (CUDA events on the rank's main stream), max over ranks"""
+    rs.step(warmup)
+    rs.sync()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms_local = rs.step_timed(steps)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t = torch.tensor([ms_local], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def bench_ranks(ek, dist, torch, args, w, local_rank):
+    """N > 1: one rank per GPU, every rank drives its x-slab through the native per-rank driver
+    (ek_rank_* of the C ABI: NCCL send/recv halos + all-to-all transposes issued from C++)."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    nbytes = ek.load_library().ek_rank_nccl_id_bytes()
+
+    def bcast(raw):
+        t = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            t.copy_(torch.tensor(list(raw), dtype=torch.uint8))
+        dist.broadcast(t, 0)
+        return bytes(t.cpu().tolist())
+
+    NX, NY, NZ = w["NX"], w["NY"], w["NZ"]
+    cells = NX * NY * NZ
+    p = ek.default_params(NX=NX, NY=NY, NZ=NZ, pb_iters=args.pb_iters, **w["over"])
+    rs = ek.RankSimulation(p, local_rank, rank, world, bcast, poisson_chunks=args.poisson_chunks)
+    rs.set_pipeline(not args.no_overlap, not args.no_overlap)
+    t0 = time.time()
+    rs.init()
+    rs.sync()
+    dist.barrier()
+    init_s = time.time() - t0
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    rs.step(args.warmup)
+    rs.sync()
+    time.sleep(0.5)
+    tw0 = time.time()
+    l0 = rs.counter("kernel_launches")
+    g0 = rs.counter("nccl_groups")
+    ms = _timed_ranks(rs, dist, torch, args.steps, args.warmup)
+    # (the warm-up steps inside _timed_ranks are counted too: per-step figures below divide by both)
+    per_step = 1.0 / (args.steps + args.warmup)
+    launches = (rs.counter("kernel_launches") - l0) * per_step
+    groups = (rs.counter("nccl_groups") - g0) * per_step
+    sampler.window(tw0, time.time())
+    clocks = sampler.stop()
+    mlups = cells * args.steps / (ms * 1e-3) / 1e6
+    zchunk_used = int(rs.counter("zchunk"))
+    K = rs.chunks()
+    nccl_version = ek.load_library().ek_rank_nccl_version()
+
+    # ---- end to end through the C ABI with HOST buffers: every rank uploads its slab of the 11
+    # macroscopic arrays from pinned memory, init_equilibrium, K steps, downloads the 11 arrays
+    e2e = None
+    if not args.no_e2e:
+        try:
+            host = {n: torch.empty(rs.shape, dtype=torch.float64, pin_memory=True).numpy() for n in ek.FIELDS}
+            for n in ek.FIELDS:
+                rs.field(n, out=host[n])
+            rs.sync()
+            dist.barrier()
+            t0 = time.perf_counter()
+            rs.set_fields(host)
+            rs.init_equilibrium()
+            rs.step(args.steps)
+            for n in ek.FIELDS:
+                rs.field(n, out=host[n])
+            rs.sync()
+            t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+            e2e = {"value": round(cells * args.steps / dt / 1e6, 2), "unit": "MLUPS",
+                   "h2d_bytes_per_step": int(11 * cells * 8 / args.steps), "d2h_bytes_per_step": int(11 * cells * 8 / args.steps),
+                   "job": f"every rank: upload its slab of 11 fields (pinned host) + init_equilibrium + {args.steps} steps + "
+                          "download 11 fields; wall clock, max over ranks", "seconds": round(dt, 4)}
+            del host
+        except Exception as exc:  # noqa: BLE001  (e.g. the pinned allocation of 11 x 1 GB per rank failed)
+            e2e = {"value": None, "unit": "MLUPS", "error": str(exc)[:200]}
+    rs.close()
+
+    # ---- config C4 (1024x256x256) strong scaling on the same ranks, against one GPU measured here
+    c4 = None
+    if not args.no_c4 and w.get("weak"):
+        try:
+            c4w = WORKLOADS["c4"]
+            p4 = ek.default_params(NX=c4w["NX"], NY=c4w["NY"], NZ=c4w["NZ"], pb_iters=min(args.pb_iters, 101), **c4w["over"])
+            cells4 = c4w["NX"] * c4w["NY"] * c4w["NZ"]
+            r4 = ek.RankSimulation(p4, local_rank, rank, world, bcast, poisson_chunks=args.poisson_chunks)
+            r4.init()
+            steps4 = max(args.steps, 40)
+            ms4 = _timed_ranks(r4, dist, torch, steps4, max(args.warmup, 10))
+            r4.close()
+            one = torch.zeros(1, dtype=torch.float64, device="cuda")
+            if rank == 0:       # the same config on ONE GPU (58 GB of populations), same start-up, same step count
+                sim = ek.Simulation(p4, device=local_rank)
+                sim.init()
+                sim.step(10)
+                one[0] = sim.step_timed(steps4)
+                sim.close()
+            dist.broadcast(one, 0)
+            ms1 = float(one.item())
+            c4 = {"workload": c4w["name"], "n_gpus": world, "steps": steps4, "ms_per_step": round(ms4 / steps4, 4),
+                  "mlups": round(cells4 * steps4 / (ms4 * 1e-3) / 1e6, 1),
+                  "one_gpu_ms_per_step": round(ms1 / steps4, 4), "one_gpu_mlups": round(cells4 * steps4 / (ms1 * 1e-3) / 1e6, 1),
+                  "speedup": round(ms1 / ms4, 3), "efficiency_vs_one_gpu": round(ms1 / ms4 / world, 4),
+                  "note": "strong scaling: the same 67 M-cell grid on N ranks (x-slabs of 1024/N columns) and on one GPU of this box"}
+        except Exception as exc:  # noqa: BLE001
+            c4 = {"error": str(exc)[:300]}
+
+    peak, peak_src = measured_peak()
+    step_gbs = mlups * 1e6 * B_ALG_STEP / 1e9
+    return {"metric": "coupled_step_mlups", "value": round(mlups, 2), "unit": "MLUPS", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4),
+            "higher_is_better": True, "scaling": "weak" if w.get("weak") else "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["name"], "grid": [NX, NY, NZ], "stream_mode": "aa", "zchunk": zchunk_used,
+                       "parallelism": f"x-slabs x{world}, one process per GPU, native driver (ek_rank.cu): NCCL {nccl_version} "
+                                      f"ncclSend/ncclRecv halos + grouped send/recv all-to-all Poisson transposes issued from C++, "
+                                      f"{K} z-chunks, forward half and way back of the Poisson stage overlapped with the LBM launches",
+                       "cells_per_gpu": cells // world, "init": "reference start-up (PB iterations) %.2f s" % init_s,
+                       "l2": "per-GPU working set >> 126 MB L2",
+                       "per_step": {"kernel_launches_per_rank": round(launches, 1), "nccl_groups_per_rank": round(groups, 1)}},
+            "roofline": {"bound": "hbm", "achieved": round(step_gbs / world, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(step_gbs / world / peak, 4), "peak_source": peak_src,
+                         "note": "whole coupled step per GPU at 1760 B/cell (kernel split is reported at N=1)",
+                         "traffic": None},
+            "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(round(launches * args.steps)), "clocks": clocks,
+            "hbm_gbs_step": round(step_gbs, 1), "extra": {"c4_strong": c4}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -220,6 +357,9 @@ def main():
     ap.add_argument("--poisson-chunks", type=int, default=4, help="N>1: z-chunks of the distributed Poisson stage")
     ap.add_argument("--transport", default="nccl", choices=["nccl", "p2p", "dma"],
                     help="N>1: Poisson transposes by NCCL all-to-all or by direct peer-memory writes (CUDA IPC)")
+    ap.add_argument("--driver", default="native", choices=["native", "python"],
+                    help="N>1: native = ek_rank.cu (NCCL driven from C++, default); python = slab.py over torch.distributed")
+    ap.add_argument("--no-c4", action="store_true", help="N>1: skip the C4 strong-scaling sub-record")
     ap.add_argument("--no-overlap", action="store_true",
                     help="N>1: do not run the Poisson forward half behind the LBM launches")
     ap.add_argument("--pb-iters", type=int, default=501,
@@ -262,9 +402,12 @@ def main():
     mode = ek.STREAM_AA if args.stream_mode == "aa" else ek.STREAM_PUSH
 
     if world > 1:
-        from importlib import import_module
-        slab = import_module("ek-pnp-3d_b200.slab")
-        result = slab.bench_slabs(ek, dist, args, w, wl, local_rank)
+        if args.driver == "python":
+            from importlib import import_module
+            slab = import_module("ek-pnp-3d_b200.slab")
+            result = slab.bench_slabs(ek, dist, args, w, wl, local_rank)
+        else:
+            result = bench_ranks(ek, dist, torch, args, w, local_rank)
         if rank == 0:
             print(json.dumps(result), flush=True)
         dist.destroy_process_group()

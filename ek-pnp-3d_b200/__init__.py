@@ -157,6 +157,23 @@ def load_library(path: str | None = None):
     L.ek_multi_slab.restype = C.c_void_p
     L.ek_multi_last_error.argtypes = [H]
     L.ek_multi_last_error.restype = C.c_char_p
+    # one process per GPU, NCCL driven from C++ (ek_rank.cu)
+    L.ek_rank_nccl_id_bytes.argtypes = []
+    L.ek_rank_nccl_unique_id.argtypes = [C.c_void_p]
+    L.ek_rank_nccl_version.argtypes = []
+    L.ek_rank_create.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(H)]
+    for name in ("ek_rank_destroy", "ek_rank_init_fields", "ek_rank_init_equilibrium", "ek_rank_init", "ek_rank_sync",
+                 "ek_rank_chunks"):
+        getattr(L, name).argtypes = [H]
+    L.ek_rank_slab.argtypes = [H]
+    L.ek_rank_slab.restype = C.c_void_p
+    L.ek_rank_set_pipeline.argtypes = [H, C.c_int, C.c_int]
+    L.ek_rank_step.argtypes = [H, C.c_int]
+    L.ek_rank_step_timed.argtypes = [H, C.c_int, C.POINTER(C.c_float)]
+    L.ek_rank_get_counter.argtypes = [H, C.c_char_p, C.POINTER(C.c_double)]
+    L.ek_rank_last_error.argtypes = [H]
+    L.ek_rank_last_error.restype = C.c_char_p
+    L.ek_is_xcheck_build.argtypes = []
     _libs[path] = L
     return L
 
@@ -452,3 +469,106 @@ class MultiSimulation:
         t = C.c_double()
         self._ck(self.L.ek_multi_read_data(self.h, path.encode(), C.byref(t)), "ek_multi_read_data")
         return t.value
+
+
+class RankSimulation:
+    """This process's x-slab of a domain split over `nranks` processes, one GPU each (ek_rank.cu):
+    halos and Poisson transposes travel over NCCL, driven from C++.  `bcast(bytes_or_None) -> bytes`
+    distributes rank 0's NCCL id block to every rank (torch.distributed, MPI, ...); every method that
+    mirrors a reference call (init, step, ...) is collective."""
+
+    def __init__(self, params: Params, device: int, rank: int, nranks: int, bcast=None, poisson_chunks: int = 0,
+                 zchunk: int | None = None):
+        self.L = load_library()
+        self.global_params = params
+        self.rank, self.nranks = int(rank), int(nranks)
+        n = self.L.ek_rank_nccl_id_bytes()
+        buf = None
+        if nranks > 1:
+            raw = None
+            if rank == 0:
+                mine = (C.c_ubyte * n)()
+                if self.L.ek_rank_nccl_unique_id(mine) != 0:
+                    raise EkError("ek_rank_nccl_unique_id failed (libnccl.so.2 not loadable?)")
+                raw = bytes(mine)
+            raw = bcast(raw)
+            buf = (C.c_ubyte * n).from_buffer_copy(raw)
+        self.r = C.c_void_p()
+        st = self.L.ek_rank_create(C.byref(params), int(device), self.rank, self.nranks, buf, int(poisson_chunks),
+                                   C.byref(self.r))
+        if st != 0:
+            self.r = C.c_void_p()
+            raise EkError(f"ek_rank_create failed: {_STATUS.get(st, st)}")
+        # a Simulation view of the slab handle (fields, options, counters); it does not own the handle
+        self.sim = Simulation.__new__(Simulation)
+        self.sim.L = self.L
+        self.sim.h = C.c_void_p(self.L.ek_rank_slab(self.r))
+        local = Params.from_buffer_copy(params)
+        local.NX = params.NX // self.nranks
+        self.sim.p = local
+        self.sim.device = int(device)
+        self.sim.shape = (local.NZ, local.NY, local.NX)
+        self.sim.ncells = local.NX * local.NY * local.NZ
+        self.sim.t = 0.0
+        self.sim.close = lambda: None
+        self.shape = self.sim.shape
+        if zchunk is not None:
+            raise EkError("zchunk of a rank is fixed at creation (ek_slab_poisson_setup)")
+
+    def _ck(self, st: int, what: str):
+        if st != 0:
+            msg = self.L.ek_rank_last_error(self.r)
+            raise EkError(f"{what}: {_STATUS.get(st, st)}: {msg.decode() if msg else ''}")
+
+    def close(self):
+        if getattr(self, "r", None) and self.r.value:
+            self.sim.h = C.c_void_p()
+            self.L.ek_rank_destroy(self.r)
+            self.r = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_pipeline(self, overlap: bool = True, overlap_back: bool = True):
+        self._ck(self.L.ek_rank_set_pipeline(self.r, int(overlap), int(overlap_back)), "ek_rank_set_pipeline")
+
+    def initialization(self):
+        self._ck(self.L.ek_rank_init_fields(self.r), "ek_rank_init_fields")
+
+    def init_equilibrium(self):
+        self._ck(self.L.ek_rank_init_equilibrium(self.r), "ek_rank_init_equilibrium")
+
+    def init(self):
+        self._ck(self.L.ek_rank_init(self.r), "ek_rank_init")
+
+    def step(self, nsteps: int = 1):
+        self._ck(self.L.ek_rank_step(self.r, int(nsteps)), "ek_rank_step")
+
+    def step_timed(self, nsteps: int) -> float:
+        ms = C.c_float()
+        self._ck(self.L.ek_rank_step_timed(self.r, int(nsteps), C.byref(ms)), "ek_rank_step_timed")
+        return ms.value
+
+    def sync(self):
+        self._ck(self.L.ek_rank_sync(self.r), "ek_rank_sync")
+
+    def counter(self, key: str) -> float:
+        v = C.c_double()
+        self._ck(self.L.ek_rank_get_counter(self.r, key.encode(), C.byref(v)), f"ek_rank_get_counter({key})")
+        return v.value
+
+    def chunks(self) -> int:
+        return self.L.ek_rank_chunks(self.r)
+
+    # this rank's columns of the macroscopic arrays, shape (NZ, NY, NX / nranks)
+    def set_fields(self, fields_local: dict):
+        self.sim.set_fields(fields_local)
+
+    def fields(self) -> dict:
+        return self.sim.fields()
+
+    def field(self, name: str, out=None):
+        return self.sim.field(name, out=out)
