@@ -260,6 +260,7 @@ def bench_ranks(ek, dist, torch, args, w, local_rank):
     mlups = cells * args.steps / (ms * 1e-3) / 1e6
     zchunk_used = int(rs.counter("zchunk"))
     K = rs.chunks()
+    phases = {"pipelined_main_stream": rs.profile(4, False), "sequential_no_overlap": rs.profile(4, True)}
     nccl_version = ek.load_library().ek_rank_nccl_version()
 
     # ---- end to end through the C ABI with HOST buffers: every rank uploads its slab of the 11
@@ -298,11 +299,17 @@ def bench_ranks(ek, dist, torch, args, w, local_rank):
             c4w = WORKLOADS["c4"]
             p4 = ek.default_params(NX=c4w["NX"], NY=c4w["NY"], NZ=c4w["NZ"], pb_iters=min(args.pb_iters, 101), **c4w["over"])
             cells4 = c4w["NX"] * c4w["NY"] * c4w["NZ"]
-            r4 = ek.RankSimulation(p4, local_rank, rank, world, bcast, poisson_chunks=args.poisson_chunks)
-            r4.init()
             steps4 = max(args.steps, 40)
-            ms4 = _timed_ranks(r4, dist, torch, steps4, max(args.warmup, 10))
-            r4.close()
+            tried = {}
+            for K4 in (2, 4):       # at 8.4 M cells per GPU the pipeline depth is a launch-count trade-off: report both
+                r4 = ek.RankSimulation(p4, local_rank, rank, world, bcast, poisson_chunks=K4)
+                r4.init()
+                tried[K4] = _timed_ranks(r4, dist, torch, steps4, max(args.warmup, 10))
+                if K4 == 4:
+                    ph4 = r4.profile(4, False)
+                r4.close()
+            K4 = min(tried, key=tried.get)
+            ms4 = tried[K4]
             one = torch.zeros(1, dtype=torch.float64, device="cuda")
             if rank == 0:       # the same config on ONE GPU (58 GB of populations), same start-up, same step count
                 sim = ek.Simulation(p4, device=local_rank)
@@ -312,7 +319,9 @@ def bench_ranks(ek, dist, torch, args, w, local_rank):
                 sim.close()
             dist.broadcast(one, 0)
             ms1 = float(one.item())
-            c4 = {"workload": c4w["name"], "n_gpus": world, "steps": steps4, "ms_per_step": round(ms4 / steps4, 4),
+            c4 = {"workload": c4w["name"], "n_gpus": world, "steps": steps4, "poisson_chunks": K4,
+                  "ms_per_step_by_chunks": {str(k): round(v / steps4, 4) for k, v in tried.items()},
+                  "phase_ms_rank0_4_chunks": ph4, "ms_per_step": round(ms4 / steps4, 4),
                   "mlups": round(cells4 * steps4 / (ms4 * 1e-3) / 1e6, 1),
                   "one_gpu_ms_per_step": round(ms1 / steps4, 4), "one_gpu_mlups": round(cells4 * steps4 / (ms1 * 1e-3) / 1e6, 1),
                   "speedup": round(ms1 / ms4, 3), "efficiency_vs_one_gpu": round(ms1 / ms4 / world, 4),
@@ -332,7 +341,8 @@ def bench_ranks(ek, dist, torch, args, w, local_rank):
                                       f"{K} z-chunks, forward half and way back of the Poisson stage overlapped with the LBM launches",
                        "cells_per_gpu": cells // world, "init": "reference start-up (PB iterations) %.2f s" % init_s,
                        "l2": "per-GPU working set >> 126 MB L2",
-                       "per_step": {"kernel_launches_per_rank": round(launches, 1), "nccl_groups_per_rank": round(groups, 1)}},
+                       "per_step": {"kernel_launches_per_rank": round(launches, 1), "nccl_groups_per_rank": round(groups, 1)},
+                       "phase_ms_rank0": phases},
             "roofline": {"bound": "hbm", "achieved": round(step_gbs / world, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(step_gbs / world / peak, 4), "peak_source": peak_src,
                          "note": "whole coupled step per GPU at 1760 B/cell (kernel split is reported at N=1)",
@@ -386,6 +396,8 @@ def main():
         import torch.distributed as dist
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"     # keep NCCL's version banner off stdout: ONE JSON line
+        # NCCL prints its banner / warnings to stdout by default: send them to stderr (stdout carries ONE JSON line)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     ek = importlib.import_module("ek-pnp-3d_b200")

@@ -171,6 +171,7 @@ def load_library(path: str | None = None):
     L.ek_rank_step.argtypes = [H, C.c_int]
     L.ek_rank_step_timed.argtypes = [H, C.c_int, C.POINTER(C.c_float)]
     L.ek_rank_get_counter.argtypes = [H, C.c_char_p, C.POINTER(C.c_double)]
+    L.ek_rank_profile.argtypes = [H, C.c_int, C.c_int, C.c_char_p, C.c_int]
     L.ek_rank_last_error.argtypes = [H]
     L.ek_rank_last_error.restype = C.c_char_p
     L.ek_is_xcheck_build.argtypes = []
@@ -562,6 +563,13 @@ class RankSimulation:
 
     def chunks(self) -> int:
         return self.L.ek_rank_chunks(self.r)
+
+    def profile(self, nsteps: int, sequential: bool) -> dict:
+        """ms per step and phase (ek_rank_profile); collective"""
+        import json
+        buf = C.create_string_buffer(4096)
+        self._ck(self.L.ek_rank_profile(self.r, int(nsteps), int(sequential), buf, 4096), "ek_rank_profile")
+        return json.loads(buf.value.decode())
 
     # this rank's columns of the macroscopic arrays, shape (NZ, NY, NX / nranks)
     def set_fields(self, fields_local: dict):

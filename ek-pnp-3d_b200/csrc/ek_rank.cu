@@ -19,6 +19,7 @@
 // The reference is single-GPU (main.cu:58); the per-step call sequence replaces main.cu:189-200.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -76,6 +77,9 @@ struct ek_rank {
     double *pto_l = nullptr, *pto_r = nullptr, *pfrom_l = nullptr, *pfrom_r = nullptr;  // phi
     bool pops = false;
     long long nccl_groups = 0;
+    // phase profile (ek_rank_profile): everything in sequence on the main stream, timed events between the phases
+    bool profile = false;
+    std::vector<std::pair<const char *, cudaEvent_t>> marks;
     std::string err;
 };
 
@@ -121,6 +125,17 @@ ek_status wait_for(ek_rank *r, cudaStream_t a, cudaStream_t b, cudaEvent_t ev)
 {
     RCUDA(r, cudaEventRecord(ev, b));
     RCUDA(r, cudaStreamWaitEvent(a, ev, 0));
+    return EK_OK;
+}
+
+// profile mode: a timed event on the main stream closes the phase `name`
+ek_status mark(ek_rank *r, const char *name)
+{
+    if (!r->profile) return EK_OK;
+    cudaEvent_t e;
+    RCUDA(r, cudaEventCreate(&e));
+    RCUDA(r, cudaEventRecord(e, r->h->stream));
+    r->marks.emplace_back(name, e);
     return EK_OK;
 }
 
@@ -225,8 +240,9 @@ ek_status poisson_rest(ek_rank *r, cudaStream_t fwd)
 {
     ek_handle *h = r->h;
     if (fwd != h->stream) RK(r, wait_for(r, h->stream, fwd, r->ev_side));
-    for (int k = 0; k < r->K; ++k) RK(r, ek_slab_poisson_gather_x(h, k));
+    RK(r, mark(r, "wait_for_forward_half"));
     RK(r, ek_slab_poisson_solve(h));
+    RK(r, mark(r, "x_fft_zsolve_x_ifft"));
     for (int k = 0; k < r->K; ++k) {
         RK(r, ek_slab_poisson_scatter_x(h, k));
         RCUDA(r, cudaEventRecord(r->ev_sc[k], h->stream));
@@ -234,18 +250,26 @@ ek_status poisson_rest(ek_rank *r, cudaStream_t fwd)
         RK(r, all_to_all(r, k, r->copy));          // chunk k travels while chunk k+1 is re-blocked
         RCUDA(r, cudaEventRecord(r->ev_landed[k], r->copy));
     }
+    RK(r, mark(r, "scatter_x"));
     return poisson_tail(r);
+}
+
+// forward half of chunk k on the handle's current stream: y-transform of my columns, transpose 1,
+// received ky blocks into my full-x pencils
+ek_status forward_chunk(ek_rank *r, int k)
+{
+    ek_handle *h = r->h;
+    RK(r, ek_slab_poisson_forward(h, k));
+    RK(r, all_to_all(r, k, h->stream));
+    RK(r, ek_slab_poisson_gather_x(h, k));
+    return EK_OK;
 }
 
 // the distributed fast_Poisson() in sequence (start-up loop): c+ - c- -> phi, ghost columns included
 ek_status poisson(ek_rank *r)
 {
-    ek_handle *h = r->h;
-    for (int k = 0; k < r->K; ++k) {
-        RK(r, ek_slab_poisson_forward(h, k));
-        RK(r, all_to_all(r, k, h->stream));
-    }
-    RK(r, poisson_rest(r, h->stream));
+    for (int k = 0; k < r->K; ++k) RK(r, forward_chunk(r, k));
+    RK(r, poisson_rest(r, r->h->stream));
     return join_back(r);
 }
 
@@ -264,15 +288,13 @@ ek_status lbm_and_forward(ek_rank *r, int full)
         if (r->overlap) {
             RCUDA(r, cudaStreamWaitEvent(r->side, r->ev_lbm[k], 0));
             OnStream on(h, r->side);
-            RK(r, ek_slab_poisson_forward(h, k));
-            RK(r, all_to_all(r, k, r->side));
+            RK(r, forward_chunk(r, k));
         }
     }
-    if (!r->overlap)
-        for (int k = 0; k < r->K; ++k) {
-            RK(r, ek_slab_poisson_forward(h, k));
-            RK(r, all_to_all(r, k, h->stream));
-        }
+    if (!r->overlap) {
+        RK(r, mark(r, "lbm"));
+        for (int k = 0; k < r->K; ++k) RK(r, forward_chunk(r, k));
+    }
     return EK_OK;
 }
 
@@ -358,8 +380,17 @@ ek_status ek_rank_create(const ek_params *global, int device, int rank, int nran
     if (st != EK_OK) return fail(st, ek_last_error(r->h));
     r->K = ek_slab_poisson_chunks(r->h);
     bool ok = true;
+    // The side streams run at the HIGHEST priority: an LBM launch keeps every SM full for milliseconds, and at
+    // equal priority the transforms / NCCL kernels queued next to it only get thread-block slots when the LBM
+    // grid drains, i.e. the "overlapped" forward half piles up behind the last LBM chunk (measured: 2.2 ms of
+    // waiting per step at 134 M cells per GPU).  With priority their blocks are scheduled as slots free up,
+    // and the NVLink transfers really travel under the LBM kernel.
+    int least = 0, greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&least, &greatest);
+    const char *prio_env = getenv("EK_RANK_PRIORITY");
+    const int prio = (prio_env && !atoi(prio_env)) ? least : greatest;
     for (cudaStream_t *s : {&r->side, &r->halo, &r->copy, &r->back})
-        ok = ok && cudaStreamCreateWithFlags(s, cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, prio) == cudaSuccess;
     auto mkev = [&](cudaEvent_t *e) { ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess; };
     for (auto *v : {&r->ev_lbm, &r->ev_sc, &r->ev_landed, &r->ev_phi}) {
         v->assign(r->K, nullptr);
@@ -450,13 +481,21 @@ ek_status ek_rank_step(ek_rank *r, int nsteps)
     for (int i = 0; i < nsteps; ++i) {
         const int full = (i == nsteps - 1);
         const int phase = ek_lbm_parity(h) == 0 ? 0 : 1;
+        RK(r, mark(r, "begin"));
         RK(r, lbm_and_forward(r, full));
+        RK(r, mark(r, r->overlap ? "lbm_launches" : "y_fft_transpose_1_gather_x"));
         // the populations travel while the Poisson stage computes (independent data)
         RK(r, halo_start(r, phase));
+        if (r->profile && !r->overlap) {   // sequential profile: the halo exchange as its own phase
+            RCUDA(r, cudaStreamWaitEvent(h->stream, r->ev_halo, 0));
+            RK(r, mark(r, "population_halos"));
+        }
         RK(r, poisson_rest(r, r->overlap ? r->side : h->stream));
         if (full || !r->overlap_back) RK(r, join_back(r));
         // else: the way back of the last chunks runs behind the next step's first LBM launches
+        RK(r, mark(r, "transpose_2_y_ifft_phi_halos"));
         RCUDA(r, cudaStreamWaitEvent(h->stream, r->ev_halo, 0));
+        RK(r, mark(r, "wait_for_population_halos"));
         if (full) RK(r, ek_compute_efield(h));
         h->steps += 1;
     }
@@ -483,6 +522,46 @@ ek_status ek_rank_step_timed(ek_rank *r, int nsteps, float *ms)
     if (st != EK_OK) return st;
     RCUDA(r, e);
     return ek_rank_sync(r);
+}
+
+// Phase split of nsteps steps as JSON {"phase": ms per step, ...} (development / DESIGN.md evidence).
+// sequential != 0: no stream overlap at all, so that every phase shows its own cost; 0: the production
+// pipeline, where a phase is what the MAIN stream waits for (overlapped work shows up as waits).
+ek_status ek_rank_profile(ek_rank *r, int nsteps, int sequential, char *json, int cap)
+{
+    if (!r || !json || cap < 64 || nsteps < 1) return EK_ERR_INVALID;
+    DeviceGuard g(r->device);
+    const bool ov = r->overlap, ovb = r->overlap_back;
+    if (sequential) { r->overlap = false; r->overlap_back = false; }
+    RK(r, ek_rank_sync(r));
+    r->profile = true;
+    ek_status st = ek_rank_step(r, nsteps);
+    r->profile = false;
+    r->overlap = ov; r->overlap_back = ovb;
+    if (st != EK_OK) return st;
+    RK(r, ek_rank_sync(r));
+    std::vector<std::pair<std::string, double>> acc;
+    for (size_t i = 1; i < r->marks.size(); ++i) {
+        if (!strcmp(r->marks[i].first, "begin")) continue;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r->marks[i - 1].second, r->marks[i].second);
+        bool found = false;
+        for (auto &a : acc)
+            if (a.first == r->marks[i].first) { a.second += ms; found = true; }
+        if (!found) acc.emplace_back(r->marks[i].first, ms);
+    }
+    for (auto &m : r->marks) cudaEventDestroy(m.second);
+    r->marks.clear();
+    std::string out = "{";
+    for (size_t i = 0; i < acc.size(); ++i) {
+        char buf[160];
+        snprintf(buf, sizeof(buf), "%s\"%s\": %.4f", i ? ", " : "", acc[i].first.c_str(), acc[i].second / nsteps);
+        out += buf;
+    }
+    out += "}";
+    if ((int)out.size() + 1 > cap) return EK_ERR_INVALID;
+    memcpy(json, out.c_str(), out.size() + 1);
+    return EK_OK;
 }
 
 // counters: "nccl_groups" (grouped send/recv calls issued), "kernel_launches", "steps"

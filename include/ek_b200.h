@@ -331,6 +331,8 @@ ek_status ek_rank_step(ek_rank *r, int nsteps);          /* main.cu:189-200 */
 ek_status ek_rank_step_timed(ek_rank *r, int nsteps, float *ms);   /* this rank's device time; max over ranks = the job's */
 ek_status ek_rank_sync(ek_rank *r);
 ek_status ek_rank_get_counter(ek_rank *r, const char *key, double *value);   /* + "nccl_groups" */
+/* phase split of nsteps steps as a JSON object of ms per step; sequential != 0 disables every overlap */
+ek_status ek_rank_profile(ek_rank *r, int nsteps, int sequential, char *json, int cap);
 const char *ek_rank_last_error(ek_rank *r);
 
 #ifdef __cplusplus
