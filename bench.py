@@ -190,6 +190,33 @@ def run_reference(args, rank: int):
         print(json.dumps(line), flush=True)
         return
     v = round(best["mlups"], 2)
+    extra = {}
+    if not args.no_extra:
+        import re
+        import tempfile
+        for name, steps2 in (("c1", 1000), ("c2", 200)):     # step-only, CUDA events around main.cu:192-198
+            exe = os.path.join(ref_dir, f"ek_ref_{name}")
+            try:
+                out = subprocess.run([exe, "--steps", str(steps2), "--warmup", "10"], check=True, capture_output=True,
+                                     text=True, timeout=600, cwd="/tmp").stdout
+                info = json.loads(out.strip().splitlines()[-1])
+                extra[name] = {"grid": [info["NX"], info["NY"], info["NZ"]], "steps": steps2, "nThreads": info["nThreads"],
+                               "us_per_step": round(1e3 * info["ms_per_step"], 2), "mlups": round(info["mlups"], 2),
+                               "init_ms": info.get("init_ms")}
+            except Exception as e:  # noqa: BLE001
+                extra[name] = {"error": str(e)[:200]}
+        # the reference exactly as shipped (unmodified main.cu: 50x8x51, 1000 steps, dumps and diagnostics inside
+        # the timed loop): its own "speed (Mlups)" line, main.cu:243,251
+        try:
+            with tempfile.TemporaryDirectory(prefix="ekstock_") as tmp:
+                out = subprocess.run([os.path.join(ref_dir, "ek_ref_stock")], input="0\n", check=True, capture_output=True,
+                                     text=True, timeout=600, cwd=tmp).stdout
+            m = re.search(r"speed:\s*([0-9.eE+-]+)\s*\(Mlups\)", out)
+            rt = re.search(r"clock runtime:\s*([0-9.eE+-]+)", out)
+            extra["c1_as_shipped"] = {"mlups": float(m.group(1)), "clock_runtime_s": float(rt.group(1)),
+                                      "note": "unmodified main.cu, I/O inside the loop (main.cu:206-222)"}
+        except Exception as e:  # noqa: BLE001
+            extra["c1_as_shipped"] = {"error": str(e)[:200]}
     line = {"impl": "reference", "metric": "coupled_step_mlups", "value": v, "unit": "MLUPS", "n_gpus": 1,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(best["ms_per_step"], 4),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -200,7 +227,8 @@ def run_reference(args, rank: int):
             "cpu_baseline": {"value": v, "unit": "MLUPS", "cores": 1, "kind": "reference",
                              "sample": "reference CUDA build (no CPU path exists), one host thread, "
                                        f"{args.steps} steps of the full C3 grid on the B200"},
-            "e2e": {"value": v, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": v, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "extra": extra}
     print(json.dumps(line), flush=True)
 
 
@@ -364,6 +392,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel", type=int, default=None, help="LBM kernel variant (ek_set_option kernel)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C1 / C2 records of the `extra` key")
     ap.add_argument("--poisson-chunks", type=int, default=4, help="N>1: z-chunks of the distributed Poisson stage")
     ap.add_argument("--transport", default="nccl", choices=["nccl", "p2p", "dma"],
                     help="N>1: Poisson transposes by NCCL all-to-all or by direct peer-memory writes (CUDA IPC)")
@@ -495,6 +524,25 @@ def main():
                "seconds": round(dt, 4)}
     sim.close()
 
+    # ---- the small configs (launch-latency bound): C1 as shipped and C2, step-only, state resident.
+    # ek_step replays a CUDA graph of two coupled steps there.  The reference's figures for the same
+    # configs are in the `extra` record of the --impl reference line.
+    extra = {}
+    if not args.no_extra:
+        for name, steps2 in (("c1", 1000), ("c2", 400)):
+            w2 = WORKLOADS[name]
+            p2 = ek.default_params(NX=w2["NX"], NY=w2["NY"], NZ=w2["NZ"], **w2["over"])
+            s2 = ek.Simulation(p2, device=local_rank)
+            s2.init()
+            s2.step(20)
+            best = min(s2.step_timed(steps2) for _ in range(3))
+            cells2 = w2["NX"] * w2["NY"] * w2["NZ"]
+            extra[name] = {"workload": w2["name"], "grid": [w2["NX"], w2["NY"], w2["NZ"]], "steps": steps2,
+                           "us_per_step": round(1e3 * best / steps2, 2), "mlups": round(cells2 * steps2 / best / 1e3, 1),
+                           "graph_replays_per_call": int(s2.counter("graph_replays")) // 3,
+                           "timing": "best of 3 x %d steps, CUDA events, macroscopic arrays written on the last step" % steps2}
+            s2.close()
+
     cb = None if args.no_cpu_baseline else cpu_baseline()
 
     line = {"metric": "coupled_step_mlups", "value": round(mlups, 2), "unit": "MLUPS", "n_gpus": 1,
@@ -503,9 +551,11 @@ def main():
             "config": {"workload": w["name"], "grid": [NX, NY, NZ], "stream_mode": args.stream_mode,
                        "zchunk": zchunk_used, "init": "reference start-up (501 PB iterations) %.2f s" % init_s,
                        "l2": "working set 14.5 GB of populations per step >> 126 MB L2 (no flush needed)",
+                       "fields": "rho, u, c+, c-, T, E are written on the last step of an ek_step(n) call (what the "
+                                 "reference's dumps read, main.cu:206); phi and c+ - c- every step",
                        "parallelism": "1 GPU"},
             "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-            "hbm_gbs_step": roofline["step_achieved"]}
+            "hbm_gbs_step": roofline["step_achieved"], "extra": extra}
     print(json.dumps(line), flush=True)
 
 

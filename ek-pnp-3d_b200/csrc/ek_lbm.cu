@@ -150,6 +150,9 @@ __device__ __forceinline__ void scalar_node(const StepArgs &a, Sh &sh, const int
     double *Wn = W + (size_t)(bottom ? 0 : 27) * c.plane;
     if (LEAN) {
         gather27_lean<MODE>(la, S);
+#ifdef EK_ODD_PREFETCH
+        if (MODE == EK_MODE_AA_ODD && z + 1 < c.NZ - 2) prefetch27_lean_odd(la, c.lplane);
+#endif
     } else if (wall) {
 #pragma unroll
         for (int d = 0; d < 27; ++d) S[d] = Wn[(size_t)d * c.plane];
@@ -319,6 +322,9 @@ __device__ __forceinline__ void fluid_node(const StepArgs &a, Sh &sh, const int 
     if (LEAN) {
         lean_set_z(la, lin, c, z);
         gather27_lean<MODE>(la, S);
+#ifdef EK_ODD_PREFETCH
+        if (MODE == EK_MODE_AA_ODD && z + 1 < c.NZ - 2) prefetch27_lean_odd(la, c.lplane);
+#endif
     } else {
         set_z(nb, c, z);
         gather27<MODE>(lin, nb, S);
