@@ -307,9 +307,9 @@ ek_status ek_set_option(ek_handle *h, const char *key, long long value)
         // 3: four warps, general path everywhere (cross-check of the lean path)
         // 5: x-marching rows with sector-aligned stores for the odd A-A step (measured slower than the
         // z-walking default; kept selectable for the A/B profile)
-        if (value < 0 || value > 5 || value == 4) return EK_ERR_INVALID;
+        if (value < 0 || value > 6 || value == 4) return EK_ERR_INVALID;   // 6: marching with aligned loads too
 #ifndef EK_XCHECK
-        if (value == 1 || value == 2) { ek_set_error(h, "kernel variants 1/2 are only in the cross-check build libek_b200_xcheck.so"); return EK_ERR_INVALID; }
+        if (value == 1 || value == 2 || value >= 5) { ek_set_error(h, "kernel variants 1, 2, 5, 6 are only in the cross-check build libek_b200_xcheck.so"); return EK_ERR_INVALID; }
 #endif
         h->kernel = (int)value;
         return EK_OK;
@@ -497,12 +497,14 @@ ek_status ek_stream_collide_save_range(ek_handle *h, int write_fields, int zbloc
     else if (h->kernel == 2) EK_CUDA(h, ek_launch_step5(a, mode, write_fields != 0, h->e_from_arrays, h->stream));
     else
 #endif
-    if (mode == EK_MODE_AA_ODD && h->kernel == 5 && !h->e_from_arrays && ek_march_applicable(h->c)) {
+#ifdef EK_XCHECK
+    if (mode == EK_MODE_AA_ODD && (h->kernel == 5 || h->kernel == 6) && !h->e_from_arrays && ek_march_applicable(h->c)) {
         // odd step: x-marching rows with sector-aligned stores (ek_lbm.cu)
         const int z0 = zblock0 * h->zchunk;
         const int z1 = zblock1 > 0 ? (zblock1 * h->zchunk < h->c.NZ ? zblock1 * h->zchunk : h->c.NZ) : h->c.NZ;
-        EK_CUDA(h, ek_launch_march(a, write_fields != 0, z0, z1, h->stream));
+        EK_CUDA(h, ek_launch_march(a, write_fields != 0, z0, z1, h->kernel == 6 ? 2 : 1, h->stream));
     } else
+#endif
     EK_CUDA(h, ek_launch_step(a, mode, write_fields != 0, h->e_from_arrays, h->kernel != 3, h->stream));
     if (h->profile) {
         EK_CUDA(h, cudaEventRecord(e1, h->stream));

@@ -196,7 +196,8 @@ void ek_slab_poisson_destroy(ek_handle *h);
 cudaError_t ek_launch_step(const StepArgs &a, int mode, bool write_fields, bool e_from_arrays, bool lean,
                            cudaStream_t st);
 // odd A-A step with sector-aligned stores (x-marching warps); planes [z0, z1) of the launch
-cudaError_t ek_launch_march(StepArgs a, bool write_fields, int z0, int z1, cudaStream_t st);
+// variant 1: aligned stores; 2: aligned loads and stores, row pointers
+cudaError_t ek_launch_march(StepArgs a, bool write_fields, int z0, int z1, int variant, cudaStream_t st);
 bool ek_march_applicable(const EkConst &c);
 cudaError_t ek_launch_step5(const StepArgs &a, int mode, bool write_fields, bool e_from_arrays, cudaStream_t st);
 cudaError_t ek_launch_step8(const StepArgs &a, int mode, bool write_fields, bool e_from_arrays, cudaStream_t st);

@@ -634,6 +634,7 @@ cudaError_t launch_mode5(const StepArgs &a, bool full, bool earr, dim3 grid, cud
 }
 #endif  // EK_XCHECK
 
+#ifdef EK_XCHECK
 // ---------------------------------------------------------------------------
 // x-marching variant of the ODD A-A step for the deep-interior planes.
 //
@@ -642,6 +643,8 @@ cudaError_t launch_mode5(const StepArgs &a, bool full, bool earr, dim3 grid, cud
 // (6912 bytes away): 9 sectors, two of them partial, per request.  Measured at 256^3 (DESIGN.md
 // 3.6): 0.31 ms of the 5.28 ms launch, the largest single loss against the even step.
 //
+// (Cross-check build only: both marching kernels are measured SLOWER than the z-walking default, DESIGN.md 3.7;
+// they are kept, bit-identical and tested, as the record of that experiment.)
 // Here a CTA (still one warp per population set) owns one (y, z) ROW and walks its x-tiles:
 //   * c_x = +1 outputs: lane i's value belongs to column i+1 -> one shuffle up; lane 0 takes what
 //     lane 31 produced for the previous tile (9 doubles per warp carried through shared memory);
@@ -904,6 +907,321 @@ __global__ void __launch_bounds__(128, EK_MIN_CTAS) ek_march_kernel(const __grid
     }
 }
 
+// ---------------------------------------------------------------------------
+// Marching kernel, second form: the LOADS are aligned as well.  Every access of a tile is then
+// "row pointer + immediate": nine row pointers (y-1..y+1 x z-1..z+1, tile T, column `lane`) advanced by
+// one tile per iteration replace the 54 neighbour addresses that the z-walking kernel re-forms for every
+// node (~135 integer instructions per thread and node, ek_lbm.cu SASS).  A population that comes from
+// x-1 is loaded from column `lane` and shuffled up one lane, lane 0 taking what lane 31 loaded for the
+// previous tile (carried in shared memory); one that comes from x+1 is shuffled down, lane 31 taking
+// column 0 of the next tile (one extra sector per request: the only unaligned access left).
+// ---------------------------------------------------------------------------
+struct March2Sm {                // per warp
+    double ring[9][64];          // c_x = -1 outputs of the tiles T-1 / T
+    double carry_st[2][9];       // lane 31's c_x = +1 outputs of tile T
+    double carry_ld[2][9];       // lane 31's loads of tile T for the directions that come from x-1
+};
+
+struct March2 {
+    double *rp[3][3];            // [kz][ky]: rows z-1..z+1, y-1..y+1 of this set: tile T, column lane, slot 0
+    LeanAddr la;                 // field offsets only (fc, fxm, fxp, fym, fyp, fdq)
+    int lane, T, NT;
+    int row0;                    // T*864 + lane: rp[..][..] - row0 is the start of the row
+    unsigned col_lo, col_hi;     // lattice offsets of the columns xlo / xhi within a row
+    March2Sm *ms;
+};
+
+__device__ __forceinline__ void march2_begin(March2 &m, const EkConst &c, double *lat, March2Sm *ms, int lane, int y, int z)
+{
+    m.lane = lane;
+    m.NT = c.NX >> 5;
+    m.T = 0;
+    m.ms = ms;
+    m.row0 = lane;
+    m.col_lo = ek_lat_col(c.xlo);
+    m.col_hi = ek_lat_col(c.xhi);
+    const int yy[3] = {y == 0 ? c.NY - 1 : y - 1, y, y == c.NY - 1 ? 0 : y + 1};
+#pragma unroll
+    for (int kz = 0; kz < 3; ++kz)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+            m.rp[kz][ky] = lat + (size_t)(z - 1 + kz) * c.lplane + (size_t)yy[ky] * c.lrow + lane;
+}
+
+__device__ __forceinline__ void march2_fields(March2 &m, const EkConst &c, int y)
+{
+    const int x = m.T * 32 + m.lane;
+    const int ym = y == 0 ? c.NY - 1 : y - 1, yp = y == c.NY - 1 ? 0 : y + 1;
+    m.la.fc = y * c.PX + x;
+    m.la.fxm = y * c.PX + (x == 0 ? c.xlo : x - 1);
+    m.la.fxp = y * c.PX + (x == c.NX - 1 ? c.xhi : x + 1);
+    m.la.fym = ym * c.PX + x;
+    m.la.fyp = yp * c.PX + x;
+    m.la.fdq = (long long)y * c.dq_sy + x;
+}
+
+__device__ __forceinline__ void march2_next(March2 &m)
+{
+#pragma unroll
+    for (int kz = 0; kz < 3; ++kz)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) m.rp[kz][ky] += EK_TILE_ELEMS;
+    m.row0 += EK_TILE_ELEMS;
+}
+
+// pre-collision populations of the node (32 T + lane, y, z): odd A-A step, S[d] = slot opp(d) at x - c_d.
+// First every load is issued (27 aligned ones and lane 31's nine next-tile elements), then the shifts run.
+template <int d>
+struct March2Load {
+    static __device__ __forceinline__ void run(const March2 &m, double S[27], double edge[9])
+    {
+        const double *q = m.rp[1 - ek_cz(d)][1 - ek_cy(d)] + ek_opp(d) * EK_TILE;
+        S[d] = EK_LD(q);
+        if (ek_cx(d) < 0) {
+            // comes from x+1: lane 31 needs column 0 of the next tile (or the column xhi at the end of the row)
+            constexpr int k = ek_xrank(d);
+            edge[k] = 0.0;
+            if (m.lane == 31) edge[k] = m.T < m.NT - 1 ? EK_LD(q + (EK_TILE_ELEMS - 31)) : EK_LD(q - m.row0 + m.col_hi);
+        }
+        March2Load<d + 1>::run(m, S, edge);
+    }
+};
+template <>
+struct March2Load<27> {
+    static __device__ __forceinline__ void run(const March2 &, double *, double *) {}
+};
+
+template <int d>
+struct March2Shift {
+    static __device__ __forceinline__ void run(const March2 &m, double S[27], const double edge[9])
+    {
+        if (ek_cx(d) > 0) {
+            constexpr int k = ek_xrank(d);
+            const double a = S[d];
+            double w = __shfl_up_sync(0xffffffffu, a, 1);
+            if (m.lane == 31) m.ms->carry_ld[m.T & 1][k] = a;
+            if (m.lane == 0) {
+                if (m.T > 0) w = m.ms->carry_ld[(m.T & 1) ^ 1][k];
+                else w = EK_LD(m.rp[1 - ek_cz(d)][1 - ek_cy(d)] + ek_opp(d) * EK_TILE - m.row0 + m.col_lo);
+            }
+            S[d] = w;
+        } else if (ek_cx(d) < 0) {
+            constexpr int k = ek_xrank(d);
+            double w = __shfl_down_sync(0xffffffffu, S[d], 1);
+            if (m.lane == 31) w = edge[k];
+            S[d] = w;
+        }
+        March2Shift<d + 1>::run(m, S, edge);
+    }
+};
+template <>
+struct March2Shift<27> {
+    static __device__ __forceinline__ void run(const March2 &, double *, const double *) {}
+};
+
+__device__ __forceinline__ void march2_gather(const March2 &m, double S[27])
+{
+    double edge[9];
+    March2Load<0>::run(m, S, edge);
+    March2Shift<1>::run(m, S, edge);
+}
+
+template <int d>
+__device__ __forceinline__ void march2_put(const March2 &m, double v)
+{
+    double *q = m.rp[1 + ek_cz(d)][1 + ek_cy(d)] + d * EK_TILE;
+    if (ek_cx(d) == 0) {
+        EK_ST(q, v);
+    } else if (ek_cx(d) > 0) {
+        constexpr int k = ek_xrank(d);
+        double w = __shfl_up_sync(0xffffffffu, v, 1);
+        if (m.lane == 31) {
+            m.ms->carry_st[m.T & 1][k] = v;
+            if (m.T == m.NT - 1) EK_ST(q - m.row0 + m.col_hi, v);   // end of the row: column xhi
+        }
+        if (m.lane == 0 && m.T > 0) w = m.ms->carry_st[(m.T & 1) ^ 1][k];
+        if (m.lane > 0 || m.T > 0) EK_ST(q, w);
+    } else {
+        constexpr int k = ek_xrank(d);
+        m.ms->ring[k][(m.T & 1) * 32 + m.lane] = v;
+        if (m.lane == 0 && m.T == 0) EK_ST(q - m.row0 + m.col_lo, v);   // start of the row: column xlo
+    }
+}
+
+template <int d>
+struct March2Drain {
+    static __device__ __forceinline__ void run(const March2 &m, bool last)
+    {
+        if (ek_cx(d) < 0) {
+            constexpr int k = ek_xrank(d);
+            const int half = last ? (m.T & 1) : ((m.T & 1) ^ 1);
+            const double w = m.ms->ring[k][(half * 32 + m.lane + 1) & 63];
+            double *q = m.rp[1 + ek_cz(d)][1 + ek_cy(d)] + d * EK_TILE;
+            if (!last) EK_ST(q - EK_TILE_ELEMS, w);
+            else if (m.lane < 31) EK_ST(q, w);
+        }
+        March2Drain<d + 1>::run(m, last);
+    }
+};
+template <>
+struct March2Drain<27> {
+    static __device__ __forceinline__ void run(const March2 &, bool) {}
+};
+
+template <int p>
+struct March2ScalarPairs {
+    static __device__ __forceinline__ void run(const double S[27], const double wcm[4], double omusq, double vtx, double vty,
+                                               double vtz, double wp, double wmn, const March2 &m)
+    {
+        constexpr int d = 2 * p + 1, o = d + 1;
+        double Oa, Ob;
+        scalar_pair_trt<d>(S, wcm, omusq, vtx, vty, vtz, wp, wmn, Oa, Ob);
+        march2_put<d>(m, Oa);
+        march2_put<o>(m, Ob);
+        March2ScalarPairs<p + 1>::run(S, wcm, omusq, vtx, vty, vtz, wp, wmn, m);
+    }
+};
+template <>
+struct March2ScalarPairs<13> {
+    static __device__ __forceinline__ void run(const double *, const double *, double, double, double, double, double,
+                                               double, const March2 &) {}
+};
+
+template <int p>
+struct March2FluidPairs {
+    static __device__ __forceinline__ void run(const double S[27], const double wcr[4], double omusq, const double u[3],
+                                               const double F[3], double uF, const EkConst &c, const March2 &m)
+    {
+        constexpr int d = 2 * p + 1, o = d + 1;
+        double Oa, Ob;
+        fluid_pair_trt<d>(S, wcr, omusq, u, F, uF, c, Oa, Ob);
+        march2_put<d>(m, Oa);
+        march2_put<o>(m, Ob);
+        March2FluidPairs<p + 1>::run(S, wcr, omusq, u, F, uF, c, m);
+    }
+};
+template <>
+struct March2FluidPairs<13> {
+    static __device__ __forceinline__ void run(const double *, const double *, double, const double *, const double *,
+                                               double, const EkConst &, const March2 &) {}
+};
+
+template <bool FULL, int NT_>
+__device__ __forceinline__ void march2_scalar_row(const StepArgs &a, Sh &sh, March2Sm *ms, const int s, const int lane,
+                                                  const int y, const int z)
+{
+    const EkConst &c = a.c;
+    const double wp = c.wp[s], wmn = c.wm[s];
+    const bool is_temp = (s == 3);
+    const double Ks = s == 1 ? c.K : c.Kn;
+    double *mom_sh = s == 1 ? sh.cp : (s == 2 ? sh.cn : sh.T);
+    March2 m;
+    march2_begin(m, c, a.in[s], ms, lane, y, z);
+    for (; m.T < m.NT; ++m.T) {
+        march2_fields(m, c, y);
+        double S[27];
+        march2_gather(m, S);
+        const double mm = sum27(S);
+        double E[3] = {0.0, 0.0, 0.0};
+        mom_sh[lane] = mm;
+        if (is_temp) {
+            efield_lean(a, m.la, z, E);
+            sh.E[0][lane] = E[0]; sh.E[1][lane] = E[1]; sh.E[2][lane] = E[2];
+        }
+        if (FULL) a.fld[3 + s][(size_t)z * c.plane + m.la.fc] = mm;   // charge, chargen, T (LBM.cu:811-813)
+        bar_moments<NT_>();
+        if (!is_temp) { E[0] = sh.E[0][lane]; E[1] = sh.E[1][lane]; E[2] = sh.E[2][lane]; }
+        bar_velocity<NT_>();
+        double vx = sh.u[0][lane], vy = sh.u[1][lane], vz = sh.u[2][lane];
+        if (!is_temp) {
+            vx = vx + Ks * E[0];
+            vy = vy + Ks * E[1];
+            vz = vz + Ks * E[2];
+        }
+        double wcm[4] = {c.w[0] * mm, c.w[1] * mm, c.w[2] * mm, c.w[3] * mm};
+        const double omusq = 1.0 - 0.5 * (vx * vx + vy * vy + vz * vz) * c.inv_cs2;
+        const double vtx = vx * c.tfac, vty = vy * c.tfac, vtz = vz * c.tfac;
+        const double O0 = S[0] - wp * (S[0] - wcm[0] * omusq);
+        m.rp[1][1][0] = O0;
+        March2ScalarPairs<0>::run(S, wcm, omusq, vtx, vty, vtz, wp, wmn, m);
+        __syncwarp();
+        if (m.T > 0) March2Drain<1>::run(m, false);
+        if (m.T < m.NT - 1) march2_next(m);
+    }
+    m.T = m.NT - 1;
+    March2Drain<1>::run(m, true);
+}
+
+template <bool FULL, int NT_>
+__device__ __forceinline__ void march2_fluid_row(const StepArgs &a, Sh &sh, March2Sm *ms, const int lane, const int y,
+                                                 const int z)
+{
+    const EkConst &c = a.c;
+    March2 m;
+    march2_begin(m, c, a.in[0], ms, lane, y, z);
+    for (; m.T < m.NT; ++m.T) {
+        march2_fields(m, c, y);
+        double S[27];
+        march2_gather(m, S);
+        const double rho = sum27(S);
+        double mo[3];
+        momentum(S, mo);
+        const double rhoinv = 1.0 / rho;
+        bar_moments<NT_>();
+        const double E[3] = {sh.E[0][lane], sh.E[1][lane], sh.E[2][lane]};
+        const double dq = sh.cp[lane] - sh.cn[lane];
+        double F[3], ex_[3], u[3];
+        node_force_and_momentum(c, mo, dq, sh.T[lane], E, F, ex_);
+        u[0] = rhoinv * ex_[0]; u[1] = rhoinv * ex_[1]; u[2] = rhoinv * ex_[2];
+        sh.u[0][lane] = u[0]; sh.u[1][lane] = u[1]; sh.u[2][lane] = u[2];
+        bar_velocity<NT_>();
+        {
+            const size_t i = (size_t)z * c.plane + m.la.fc;
+            a.dq[(size_t)z * c.dq_sz + m.la.fdq] = dq;
+            if (FULL) {  // LBM.cu:807-810
+                a.fld[0][i] = rho; a.fld[1][i] = u[0]; a.fld[2][i] = u[1]; a.fld[3][i] = u[2];
+            }
+        }
+        double wcr[4] = {c.w[0] * rho, c.w[1] * rho, c.w[2] * rho, c.w[3] * rho};
+        const double omusq = 1.0 - 0.5 * (u[0] * u[0] + u[1] * u[1] + u[2] * u[2]) * c.inv_cs2;
+        const double uF = u[0] * F[0] + u[1] * F[1] + u[2] * F[2];
+        const double O0 = S[0] - c.wp[0] * (S[0] - wcr[0] * omusq) + c.dt * (c.sp * (-c.coe[0] * uF));
+        m.rp[1][1][0] = O0;
+        March2FluidPairs<0>::run(S, wcr, omusq, u, F, uF, c, m);
+        __syncwarp();
+        if (m.T > 0) March2Drain<1>::run(m, false);
+        if (m.T < m.NT - 1) march2_next(m);
+    }
+    m.T = m.NT - 1;
+    March2Drain<1>::run(m, true);
+}
+
+template <bool FULL>
+__global__ void __launch_bounds__(128, EK_MIN_CTAS) ek_march2_kernel(const __grid_constant__ StepArgs a)
+{
+    __shared__ Sh sh;
+    __shared__ March2Sm msm[4];
+    const EkConst &c = a.c;
+    const int lane = threadIdx.x & 31;
+    const int role = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int y = blockIdx.x;
+    if ((int)blockIdx.y < a.march_planes) {
+        const int z = a.march_z0 + blockIdx.y;
+        if (role == 0) march2_fluid_row<FULL, 128>(a, sh, &msm[0], lane, y, z);
+        else march2_scalar_row<FULL, 128>(a, sh, &msm[role], role, lane, y, z);
+    } else {
+        const int w = blockIdx.y - a.march_planes, NT = c.NX >> 5;
+        const int side = w / NT, tile = w - side * NT;
+        const int x = tile * 32 + lane;
+        const int z0 = a.wall_z0[side], z1 = a.wall_z1[side];
+        const int pi = y * c.PX + x;
+        if (role == 0) fluid_role<EK_MODE_AA_ODD, FULL, 128, false>(a, sh, lane, true, x, y, z0, z1);
+        else scalar_role<EK_MODE_AA_ODD, FULL, false, 128, false>(a, sh, role, lane, true, x, y, pi, z0, z1);
+    }
+}
+
+#endif  // EK_XCHECK (marching kernels)
+
 template <int MODE>
 cudaError_t launch_mode(const StepArgs &a, bool full, bool earr, bool lean, dim3 grid, cudaStream_t st)
 {
@@ -934,11 +1252,12 @@ cudaError_t ek_launch_step(const StepArgs &a, int mode, bool write_fields, bool 
     }
 }
 
+#ifdef EK_XCHECK
 bool ek_march_applicable(const EkConst &c) { return (c.NX % 32) == 0 && c.NZ >= 6; }
 
 // odd A-A step of the planes [z0, z1): x-marching rows for the deep interior (2 <= z <= NZ-3), the general
 // node path for the wall-adjacent planes, in ONE launch
-cudaError_t ek_launch_march(StepArgs a, bool write_fields, int z0, int z1, cudaStream_t st)
+cudaError_t ek_launch_march(StepArgs a, bool write_fields, int z0, int z1, int variant, cudaStream_t st)
 {
     const EkConst &c = a.c;
     const int m0 = z0 > 2 ? z0 : 2, m1 = z1 < c.NZ - 2 ? z1 : c.NZ - 2;
@@ -958,6 +1277,8 @@ cudaError_t ek_launch_march(StepArgs a, bool write_fields, int z0, int z1, cudaS
         if (pct >= 0) {
             cudaFuncSetAttribute(ek_march_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
             cudaFuncSetAttribute(ek_march_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            cudaFuncSetAttribute(ek_march2_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            cudaFuncSetAttribute(ek_march2_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
         }
         if (getenv("EK_DEBUG")) {
             int nb = 0;
@@ -966,12 +1287,16 @@ cudaError_t ek_launch_march(StepArgs a, bool write_fields, int z0, int z1, cudaS
         }
         configured = true;
     }
-    if (write_fields) ek_march_kernel<true><<<grid, 128, 0, st>>>(a);
-    else ek_march_kernel<false><<<grid, 128, 0, st>>>(a);
+    if (variant == 2) {
+        if (write_fields) ek_march2_kernel<true><<<grid, 128, 0, st>>>(a);
+        else ek_march2_kernel<false><<<grid, 128, 0, st>>>(a);
+    } else {
+        if (write_fields) ek_march_kernel<true><<<grid, 128, 0, st>>>(a);
+        else ek_march_kernel<false><<<grid, 128, 0, st>>>(a);
+    }
     return cudaGetLastError();
 }
 
-#ifdef EK_XCHECK
 cudaError_t ek_launch_step5(const StepArgs &a, int mode, bool write_fields, bool e_from_arrays, cudaStream_t st)
 {
     const EkConst &c = a.c;

@@ -151,10 +151,11 @@ ek_status ek_set_poisson_dc(ek_handle *h, int mode, double ghat0);
  * "graph" (ek_step replays a CUDA graph of two coupled steps: 1 on, 0 off,
  * -1 automatic = grids below 4 M cells, which are launch-latency bound),
  * "kernel" (0 default: z-walking CTAs with the lean deep-interior node path; 3: general node
- * path everywhere; 5: x-marching rows with sector-aligned stores for the odd A-A step).
+ * path everywhere).
  * Cross-check build only (libek_b200_xcheck.so, ek_is_xcheck_build()):
  * "poisson_path" 1 = the reference's odd-extension 3-D FFT (poisson.cu:75-103
- * literally), "kernel" 1/2 = eight-/five-warp LBM kernels, EK_DC_LITERAL. */
+ * literally), "kernel" 1/2 = eight-/five-warp LBM kernels, 5/6 = x-marching rows for the odd
+ * A-A step (aligned stores / aligned loads and stores), EK_DC_LITERAL. */
 ek_status ek_set_option(ek_handle *h, const char *key, long long value);
 /* counters: "steps", "zchunk", "lbm_launches", "poisson_launches", "kernel_launches";
  * times (ms, profile on): "lbm_ms", "poisson_ms" */

@@ -229,7 +229,7 @@ def test_product_library_has_no_cross_check_variants(ek):
     assert ek.load_library().ek_is_xcheck_build() == 0
     assert ek.load_library(ek.XCHECK_LIB_PATH).ek_is_xcheck_build() == 1
     sim = ek.Simulation(ek.default_params(NX=8, NY=2, NZ=7))
-    for key, value in (("kernel", 1), ("kernel", 2), ("poisson_path", 1)):
+    for key, value in (("kernel", 1), ("kernel", 2), ("kernel", 5), ("kernel", 6), ("poisson_path", 1)):
         with pytest.raises(ek.EkError):
             sim.set_option(key, value)
     with pytest.raises(ek.EkError):
@@ -545,16 +545,16 @@ def test_reference_signature_shim(ek):
 
 @pytest.mark.parametrize("NX", [40, 64, 96])
 def test_kernel_variants_agree(ek, NX):
-    """LBM kernel variants: 0 (default: z-walking CTAs, lean deep-interior path), 5 (x-marching rows
-    with sector-aligned stores for the odd A-A step when NX % 32 == 0), 3 (general node path
+    """LBM kernel variants: 0 (default: z-walking CTAs, lean deep-interior path), 5 / 6 (x-marching rows
+    for the odd A-A step when NX % 32 == 0: sector-aligned stores / aligned loads too), 3 (general node path
     everywhere) and the cross-check build's five-warp kernel 2 chain the sums in the reference's
     order and must agree bit for bit; the eight-warp kernel 1 adds two partial sums."""
     over = dict(NX=NX, NY=5, NZ=21, uw=1.0e-4, exf=1.0e6)
     init = synthetic_init(over)
     res = {}
-    for kernel in (0, 1, 2, 3, 5):
+    for kernel in (0, 1, 2, 3, 5, 6):
         for mode in (ek.STREAM_AA, ek.STREAM_PUSH):
-            sim = ek.Simulation(ek.default_params(**over), stream_mode=mode, zchunk=6, xcheck=kernel in (1, 2))
+            sim = ek.Simulation(ek.default_params(**over), stream_mode=mode, zchunk=6, xcheck=kernel in (1, 2, 5, 6))
             sim.set_option("kernel", kernel)
             sim.set_option("graph", 0)
             sim.set_fields(init)
@@ -583,22 +583,23 @@ def test_marching_odd_step_in_z_ranges_and_with_fields(ek):
     over = dict(NX=64, NY=6, NZ=23, exf=1.0e6)
     init = synthetic_init(over)
     res = []
-    for kernel in (0, 5):
-        sim = ek.Simulation(ek.default_params(**over), zchunk=4)
+    for kernel in (0, 5, 6):
+        sim = ek.Simulation(ek.default_params(**over), zchunk=4, xcheck=kernel >= 5)
         sim.set_option("kernel", kernel)
         sim.set_fields(init)
         sim.init_equilibrium()
         nb = -(-23 // 4)
         for step in range(6):
-            cuts = [0, 1, 3, nb] if kernel == 5 else [0, nb]
+            cuts = [0, 1, 3, nb] if kernel >= 5 else [0, nb]
             for b0, b1 in zip(cuts[:-1], cuts[1:]):
                 sim._ck(sim.L.ek_stream_collide_save_range(sim.h, 1, b0, b1, int(b1 == nb)), "range")
             sim.fast_Poisson(True)
         res.append((sim.fields(), np.stack([sim.populations(s) for s in range(4)])))
         sim.close()
-    for k in util.FIELDS:
-        assert np.array_equal(res[0][0][k], res[1][0][k]), k
-    assert np.array_equal(res[0][1], res[1][1])
+    for other in res[1:]:
+        for k in util.FIELDS:
+            assert np.array_equal(res[0][0][k], other[0][k]), k
+        assert np.array_equal(res[0][1], other[1])
 
 
 # ---------------------------------------------------------------------------
