@@ -87,6 +87,7 @@ def load_library(path: str | None = None):
     L.ek_step_timed.argtypes = [H, C.c_int, C.POINTER(C.c_float)]
     L.ek_stream_collide_save.argtypes = [H, C.c_int]
     L.ek_stream_collide_save_range.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.ek_stream_collide_save_part.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     L.ek_switch_stream.argtypes = [H, C.c_void_p]
     L.ek_fast_poisson.argtypes = [H, C.c_int]
     L.ek_get_field.argtypes = [H, C.c_int, C.c_void_p, C.c_int]

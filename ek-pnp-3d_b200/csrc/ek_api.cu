@@ -478,6 +478,14 @@ ek_status ek_stream_collide_save(ek_handle *h, int write_fields)
 // disjoint); `last` != 0 on the final launch of the pass advances the parity.
 ek_status ek_stream_collide_save_range(ek_handle *h, int write_fields, int zblock0, int zblock1, int last)
 {
+    return ek_stream_collide_save_part(h, write_fields, zblock0, zblock1, 0, last);
+}
+
+// The same restricted in x as well: xtiles = 0 every 32-column tile of a row, 1 the two boundary tiles (first
+// and last), 2 the interior tiles.  The slab pipeline launches the boundary tiles of the whole pass first and
+// sends the population halos under the launches of the interior tiles (default kernel only).
+ek_status ek_stream_collide_save_part(ek_handle *h, int write_fields, int zblock0, int zblock1, int xtiles, int last)
+{
     if (!h) return EK_ERR_INVALID;
     if (!h->pops_ready) { ek_set_error(h, "ek_stream_collide_save before ek_init_equilibrium"); return EK_ERR_STATE; }
     const int nblocks = (h->c.NZ + h->zchunk - 1) / h->zchunk;
@@ -486,6 +494,8 @@ ek_status ek_stream_collide_save_range(ek_handle *h, int write_fields, int zbloc
     StepArgs a = ek_step_args(h);
     a.zblock0 = zblock0;
     a.nzblocks = zblock1 > 0 ? zblock1 - zblock0 : 0;
+    if (xtiles < 0 || xtiles > 2 || (xtiles != 0 && h->kernel != 0 && h->kernel != 3)) return EK_ERR_INVALID;
+    a.xt_mode = xtiles;
     const int mode = h->stream_mode == EK_STREAM_PUSH ? EK_MODE_PUSH : (h->parity ? EK_MODE_AA_ODD : EK_MODE_AA_EVEN);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->profile) {

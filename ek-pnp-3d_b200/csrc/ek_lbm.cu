@@ -428,7 +428,11 @@ __global__ void __launch_bounds__(128, EK_MIN_CTAS) ek_step_kernel(const __grid_
     // broadcast through a shuffle: tells the compiler that the role is warp-uniform, so that the role's
     // loop counters, plane bases and branches can live in the uniform datapath
     const int role = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
-    int x = blockIdx.x * 32 + lane;
+    // x-tile of this CTA: all tiles, or -- slab pipeline -- the two boundary tiles of the row first, so that the
+    // halo exchange travels under the launch of the interior tiles
+    const int xtile = a.xt_mode == 0 ? (int)blockIdx.x
+                    : (a.xt_mode == 1 ? (blockIdx.x == 0 ? 0 : (c.NX + 31) / 32 - 1) : (int)blockIdx.x + 1);
+    int x = xtile * 32 + lane;
     const bool act = x < c.NX;
     if (!act) x = c.NX - 1;  // clamped duplicate: loads stay in bounds, stores are masked
     const int y = blockIdx.y;
@@ -1244,7 +1248,10 @@ cudaError_t ek_launch_step(const StepArgs &a, int mode, bool write_fields, bool 
                            cudaStream_t st)
 {
     const EkConst &c = a.c;
-    dim3 grid((c.NX + 31) / 32, c.NY, a.nzblocks > 0 ? a.nzblocks : (c.NZ + a.zchunk - 1) / a.zchunk);
+    const int NT = (c.NX + 31) / 32;
+    const int nxt = a.xt_mode == 0 ? NT : (a.xt_mode == 1 ? (NT < 2 ? NT : 2) : NT - 2);
+    if (nxt <= 0) return cudaSuccess;
+    dim3 grid(nxt, c.NY, a.nzblocks > 0 ? a.nzblocks : (c.NZ + a.zchunk - 1) / a.zchunk);
     switch (mode) {
     case EK_MODE_AA_EVEN: return launch_mode<EK_MODE_AA_EVEN>(a, write_fields, e_from_arrays, lean, grid, st);
     case EK_MODE_AA_ODD: return launch_mode<EK_MODE_AA_ODD>(a, write_fields, e_from_arrays, lean, grid, st);

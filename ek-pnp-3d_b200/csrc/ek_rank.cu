@@ -70,9 +70,10 @@ struct ek_rank {
     ncclComm_t comm[NCOMM] = {nullptr, nullptr, nullptr};
     cudaStream_t side = nullptr, halo = nullptr, copy = nullptr, back = nullptr;
     std::vector<cudaEvent_t> ev_lbm, ev_sc, ev_landed, ev_phi;
-    cudaEvent_t ev_side = nullptr, ev_main = nullptr, ev_halo = nullptr, ev_back = nullptr;
+    cudaEvent_t ev_side = nullptr, ev_main = nullptr, ev_halo = nullptr, ev_back = nullptr, ev_bnd = nullptr;
     bool have_phi_ready = false;
     bool overlap = true, overlap_back = true;
+    bool boundary_first = true;   // LBM pass: boundary x-tiles first, population halos under the interior launches
     double *to_l = nullptr, *to_r = nullptr, *from_l = nullptr, *from_r = nullptr;      // populations
     double *pto_l = nullptr, *pto_r = nullptr, *pfrom_l = nullptr, *pfrom_r = nullptr;  // phi
     bool pops = false;
@@ -191,10 +192,10 @@ void chunk_planes(ek_rank *r, int k, int *z0, int *z1)
     *z1 = S.block0[k + 1] * zc < NZ ? S.block0[k + 1] * zc : NZ;
 }
 
-ek_status halo_start(ek_rank *r, int phase)
+ek_status halo_start(ek_rank *r, int phase, cudaEvent_t after)
 {
     ek_handle *h = r->h;
-    RCUDA(r, cudaStreamWaitEvent(r->halo, r->ev_lbm[r->K - 1], 0));   // after this rank's LBM pass
+    RCUDA(r, cudaStreamWaitEvent(r->halo, after, 0));   // after the launches that touch the boundary / ghost columns
     OnStream on(h, r->halo);
     RK(r, ek_halo_pack(h, phase, r->to_l, r->to_r));
     RK(r, ring_exchange(r, COMM_H, r->to_l, r->to_r, r->from_l, r->from_r, (size_t)ek_halo_doubles(h), r->halo));
@@ -274,16 +275,31 @@ ek_status poisson(ek_rank *r)
 }
 
 // One LBM pass launched chunk by chunk; chunk k's forward half runs on the side stream behind the
-// launches of the later chunks
-ek_status lbm_and_forward(ek_rank *r, int full)
+// launches of the later chunks.  With boundary_first the two boundary x-tiles of every row are launched
+// before the interior ones and the population halos (pack -> NCCL -> unpack, which only touch the boundary
+// and ghost columns) travel under the interior launches.
+ek_status lbm_and_forward(ek_rank *r, int full, int phase)
 {
     ek_handle *h = r->h;
     const EkSlabPoisson &S = h->sp;
-    for (int k = 0; k < r->K; ++k) {
-        // the planes of chunk k take grad(phi) from the chunks k-1 .. k+1 of the previous solve, whose way
-        // back may still be running on the back stream
+    const bool split = r->boundary_first && (h->c.NX + 31) / 32 >= 3 && (h->kernel == 0 || h->kernel == 3);
+    // the planes of chunk k take grad(phi) from the chunks k-1 .. k+1 of the previous solve, whose way
+    // back may still be running on the back stream
+    auto wait_phi = [&](int k) -> ek_status {
         if (r->have_phi_ready) RCUDA(r, cudaStreamWaitEvent(h->stream, r->ev_phi[k + 1 < r->K ? k + 1 : r->K - 1], 0));
-        RK(r, ek_stream_collide_save_range(h, full, S.block0[k], S.block0[k + 1], k == r->K - 1));
+        return EK_OK;
+    };
+    if (split) {
+        for (int k = 0; k < r->K; ++k) {
+            RK(r, wait_phi(k));
+            RK(r, ek_stream_collide_save_part(h, full, S.block0[k], S.block0[k + 1], 1, 0));
+        }
+        RCUDA(r, cudaEventRecord(r->ev_bnd, h->stream));
+        RK(r, halo_start(r, phase, r->ev_bnd));
+    }
+    for (int k = 0; k < r->K; ++k) {
+        if (!split) RK(r, wait_phi(k));
+        RK(r, ek_stream_collide_save_part(h, full, S.block0[k], S.block0[k + 1], split ? 2 : 0, k == r->K - 1));
         RCUDA(r, cudaEventRecord(r->ev_lbm[k], h->stream));
         if (r->overlap) {
             RCUDA(r, cudaStreamWaitEvent(r->side, r->ev_lbm[k], 0));
@@ -291,6 +307,7 @@ ek_status lbm_and_forward(ek_rank *r, int full)
             RK(r, forward_chunk(r, k));
         }
     }
+    if (!split) RK(r, halo_start(r, phase, r->ev_lbm[r->K - 1]));
     if (!r->overlap) {
         RK(r, mark(r, "lbm"));
         for (int k = 0; k < r->K; ++k) RK(r, forward_chunk(r, k));
@@ -311,7 +328,7 @@ void release(ek_rank *r)
         if (s) cudaStreamDestroy(s);
     for (auto *v : {&r->ev_lbm, &r->ev_sc, &r->ev_landed, &r->ev_phi})
         for (cudaEvent_t e : *v) cudaEventDestroy(e);
-    for (cudaEvent_t e : {r->ev_side, r->ev_main, r->ev_halo, r->ev_back})
+    for (cudaEvent_t e : {r->ev_side, r->ev_main, r->ev_halo, r->ev_back, r->ev_bnd})
         if (e) cudaEventDestroy(e);
     for (double *p : {r->to_l, r->to_r, r->from_l, r->from_r, r->pto_l, r->pto_r, r->pfrom_l, r->pfrom_r}) cudaFree(p);
     if (r->h) ek_destroy(r->h);
@@ -396,7 +413,9 @@ ek_status ek_rank_create(const ek_params *global, int device, int rank, int nran
         v->assign(r->K, nullptr);
         for (int k = 0; k < r->K; ++k) mkev(&(*v)[k]);
     }
-    for (cudaEvent_t *e : {&r->ev_side, &r->ev_main, &r->ev_halo, &r->ev_back}) mkev(e);
+    for (cudaEvent_t *e : {&r->ev_side, &r->ev_main, &r->ev_halo, &r->ev_back, &r->ev_bnd}) mkev(e);
+    const char *bf = getenv("EK_RANK_BOUNDARY_FIRST");
+    if (bf) r->boundary_first = atoi(bf) != 0;
     const size_t nh = (size_t)ek_halo_doubles(r->h) * sizeof(double);
     const size_t np = (size_t)global->NY * global->NZ * sizeof(double);
     for (double **p : {&r->to_l, &r->to_r, &r->from_l, &r->from_r}) ok = ok && cudaMalloc((void **)p, nh) == cudaSuccess;
@@ -482,10 +501,9 @@ ek_status ek_rank_step(ek_rank *r, int nsteps)
         const int full = (i == nsteps - 1);
         const int phase = ek_lbm_parity(h) == 0 ? 0 : 1;
         RK(r, mark(r, "begin"));
-        RK(r, lbm_and_forward(r, full));
+        // (the population halos are started in there: under the interior launches, or after the pass)
+        RK(r, lbm_and_forward(r, full, phase));
         RK(r, mark(r, r->overlap ? "lbm_launches" : "y_fft_transpose_1_gather_x"));
-        // the populations travel while the Poisson stage computes (independent data)
-        RK(r, halo_start(r, phase));
         if (r->profile && !r->overlap) {   // sequential profile: the halo exchange as its own phase
             RCUDA(r, cudaStreamWaitEvent(h->stream, r->ev_halo, 0));
             RK(r, mark(r, "population_halos"));

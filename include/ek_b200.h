@@ -105,6 +105,9 @@ ek_status ek_fast_poisson(ek_handle *h, int write_efield);
  * "zchunk" planes each (0,0 = all); last != 0 on the final launch of a pass.
  * Lets the host pipeline the distributed Poisson stage against the LBM pass. */
 ek_status ek_stream_collide_save_range(ek_handle *h, int write_fields, int zblock0, int zblock1, int last);
+/* ... and over a subset of the 32-column x-tiles of every row: xtiles = 0 all, 1 the two boundary tiles (first and
+ * last), 2 the interior ones -- boundary tiles first, so that the halo exchange travels under the interior launch */
+ek_status ek_stream_collide_save_part(ek_handle *h, int write_fields, int zblock0, int zblock1, int xtiles, int last);
 
 /* ek_step bracketed by CUDA events on the handle's stream; blocks until done
  * and returns the device time of the nsteps steps in milliseconds. */

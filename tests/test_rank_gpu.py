@@ -21,9 +21,11 @@ def ek():
     return util.ek_module()
 
 
-@pytest.mark.parametrize("chunks", [1, 3])
-def test_single_rank_matches_the_single_domain_run_and_the_oracle(ek, chunks):
-    over = dict(NX=64, NY=6, NZ=21, exf=1.0e6, uw=1.0e-4, voltage2=-3.0e-3)
+@pytest.mark.parametrize("chunks,NX", [(1, 64), (3, 64), (3, 96), (2, 128)])
+def test_single_rank_matches_the_single_domain_run_and_the_oracle(ek, chunks, NX):
+    """NX >= 96: three or more x-tiles per row, so the LBM pass is launched boundary tiles first and the
+    halo exchange runs under the interior launches"""
+    over = dict(NX=NX, NY=6, NZ=21, exf=1.0e6, uw=1.0e-4, voltage2=-3.0e-3)
     init = synthetic_init(over)
     want, _ = product_run(ek, over, init, 7, ek.STREAM_AA)
     ref, _ = oracle_run(over, init, 7)

@@ -50,6 +50,7 @@ def main():
     ok = True
     cases = {
         "generic": dict(NX=64 * world, NY=12, NZ=21, pb_iters=30, exf=1.0e6, uw=1.0e-4, voltage2=-3.0e-3),
+        "three_tiles_per_rank": dict(NX=96 * world, NY=6, NZ=21, pb_iters=30, exf=1.0e6, voltage2=-3.0e-3),
         "c4_shaped": dict(NX=1024, NY=8, NZ=37, pb_iters=30, exf=2.0e6, chargeinf=0.002),
     }
     for name, over in cases.items():
