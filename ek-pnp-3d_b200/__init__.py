@@ -169,6 +169,7 @@ def load_library(path: str | None = None):
     L.ek_rank_slab.argtypes = [H]
     L.ek_rank_slab.restype = C.c_void_p
     L.ek_rank_set_pipeline.argtypes = [H, C.c_int, C.c_int]
+    L.ek_rank_set_boundary_first.argtypes = [H, C.c_int]
     L.ek_rank_step.argtypes = [H, C.c_int]
     L.ek_rank_step_timed.argtypes = [H, C.c_int, C.POINTER(C.c_float)]
     L.ek_rank_get_counter.argtypes = [H, C.c_char_p, C.POINTER(C.c_double)]
@@ -481,6 +482,10 @@ class RankSimulation:
 
     def __init__(self, params: Params, device: int, rank: int, nranks: int, bcast=None, poisson_chunks: int = 0,
                  zchunk: int | None = None):
+        try:        # if PyTorch is around, let ITS libnccl.so.2 be the one in the process: ek_rank.cu dlopens NCCL by
+            import torch  # noqa: F401  (SONAME, and a system copy loaded first would shadow the one torch needs)
+        except ImportError:
+            pass
         self.L = load_library()
         self.global_params = params
         self.rank, self.nranks = int(rank), int(nranks)
@@ -534,8 +539,10 @@ class RankSimulation:
         except Exception:
             pass
 
-    def set_pipeline(self, overlap: bool = True, overlap_back: bool = True):
+    def set_pipeline(self, overlap: bool = True, overlap_back: bool = True, boundary_first: bool | None = None):
         self._ck(self.L.ek_rank_set_pipeline(self.r, int(overlap), int(overlap_back)), "ek_rank_set_pipeline")
+        if boundary_first is not None:
+            self._ck(self.L.ek_rank_set_boundary_first(self.r, int(boundary_first)), "ek_rank_set_boundary_first")
 
     def initialization(self):
         self._ck(self.L.ek_rank_init_fields(self.r), "ek_rank_init_fields")

@@ -8,6 +8,7 @@ import sys
 
 import numpy as np
 import pytest
+import torch  # noqa: F401  (before anything dlopens libnccl.so.2: PyTorch needs its own copy)
 
 from tests import util
 from tests.test_oracle_cpu import check
@@ -30,10 +31,10 @@ def test_single_rank_matches_the_single_domain_run_and_the_oracle(ek, chunks, NX
     want, _ = product_run(ek, over, init, 7, ek.STREAM_AA)
     ref, _ = oracle_run(over, init, 7)
     res = []
-    for overlap in (True, False):
+    for overlap, bfirst in ((True, True), (False, False), (True, False)):
         rs = ek.RankSimulation(ek.default_params(**over), 0, 0, 1, None, poisson_chunks=chunks)
         assert rs.chunks() == chunks
-        rs.set_pipeline(overlap, overlap)
+        rs.set_pipeline(overlap, overlap, boundary_first=bfirst)
         rs.set_fields(init)
         rs.init_equilibrium()
         rs.step(4)
@@ -43,8 +44,9 @@ def test_single_rank_matches_the_single_domain_run_and_the_oracle(ek, chunks, NX
         rs.close()
     check(util.field_errors(res[0], want))
     check(util.field_errors(res[0], ref))
-    for k in util.FIELDS:
-        assert np.array_equal(res[0][k], res[1][k]), k      # pipelined == sequential, bit for bit
+    for other in res[1:]:
+        for k in util.FIELDS:
+            assert np.array_equal(res[0][k], other[k]), k      # pipelined / boundary-first == sequential, bit for bit
 
 
 def test_single_rank_startup_timed_steps_and_profile(ek):

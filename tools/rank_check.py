@@ -65,7 +65,7 @@ def main():
         res = {}
         for overlap in (True, False):
             rs = ek.RankSimulation(ek.default_params(**over), local, rank, world, bcast, poisson_chunks=3)
-            rs.set_pipeline(overlap, overlap)
+            rs.set_pipeline(overlap, overlap, boundary_first=overlap)
             rs.set_fields({k: np.ascontiguousarray(v[:, :, rank * w:(rank + 1) * w]) for k, v in init.items()})
             rs.init_equilibrium()
             rs.step(4)
