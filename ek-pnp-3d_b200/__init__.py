@@ -84,6 +84,7 @@ def load_library(path: str | None = None):
         getattr(L, name).argtypes = [H]
     L.ek_set_fields.argtypes = [H, C.POINTER(C.c_void_p), C.c_int]
     L.ek_step.argtypes = [H, C.c_int]
+    L.ek_run_from_host.argtypes = [H, C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]
     L.ek_step_timed.argtypes = [H, C.c_int, C.POINTER(C.c_float)]
     L.ek_stream_collide_save.argtypes = [H, C.c_int]
     L.ek_stream_collide_save_range.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -303,6 +304,29 @@ class Simulation:
         """nsteps iterations of the loop body main.cu:189-200."""
         self._ck(self.L.ek_step(self.h, int(nsteps)), "ek_step")
         self.t += nsteps * self.p.dt
+
+    def run_from_host(self, fields_in: dict, nsteps: int, fields_out: dict | None = None) -> dict:
+        """One whole job on host arrays (ek_run_from_host): upload the 11 arrays, init_equilibrium(), nsteps
+        steps, download the 11 arrays, with the PCIe copies overlapped with the first and last LBM pass.
+        fields_out: preallocated (ideally pinned) arrays to fill; returned."""
+        src = (C.c_void_p * len(FIELDS))()
+        dst = (C.c_void_p * len(FIELDS))()
+        keep = []
+        out = fields_out if fields_out is not None else {}
+        for i, n in enumerate(FIELDS):
+            a = np.ascontiguousarray(fields_in[n], dtype=np.float64)
+            if a.size != self.ncells:
+                raise ValueError(f"field {n}: expected {self.ncells} values, got {a.size}")
+            keep.append(a)
+            src[i] = a.ctypes.data
+            if n not in out:
+                out[n] = np.empty(self.shape, dtype=np.float64)
+            if out[n].size != self.ncells or not out[n].flags["C_CONTIGUOUS"] or out[n].dtype != np.float64:
+                raise ValueError(f"output array {n} must be a contiguous float64 array of {self.ncells} values")
+            dst[i] = out[n].ctypes.data
+        self._ck(self.L.ek_run_from_host(self.h, src, int(nsteps), dst), "ek_run_from_host")
+        self.t += nsteps * self.p.dt
+        return out
 
     def step_timed(self, nsteps: int) -> float:
         """step(nsteps) bracketed by CUDA events on the handle's stream; returns ms."""

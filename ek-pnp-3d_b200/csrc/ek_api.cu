@@ -267,6 +267,8 @@ ek_status ek_destroy(ek_handle *h)
     cudaStreamSynchronize(h->stream);
     collect_events(h);
     if (h->pair_graph) cudaGraphExecDestroy(h->pair_graph);
+    for (cudaEvent_t e : h->job_events) cudaEventDestroy(e);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     free_state(h);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -628,6 +630,113 @@ ek_status ek_step(ek_handle *h, int nsteps)
         if (st != EK_OK) return st;
         ++i;
     }
+    return EK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// One whole job on HOST arrays: what a caller with its fields in host memory does with
+// ek_set_fields + ek_init_equilibrium + ek_step(n) + 11 x ek_get_field, as ONE call whose PCIe
+// copies overlap the device work instead of bracketing it:
+//   * the upload runs plane group by plane group on a copy stream; as soon as a group has landed its
+//     populations are initialised and the FIRST LBM pass runs on it (the first pass is the even A-A
+//     step, node-local, and takes E from the uploaded arrays, main.cu:174,192): the start-up kernels
+//     and one of the n LBM passes hide under the upload;
+//   * the LAST LBM pass is launched group by group and the rho, u, c+, c-, T planes it writes are
+//     downloaded behind it; phi and E follow after the last solve.
+// Same results as the plain sequence, bit for bit (tests).  Host buffers should be pinned.
+// ---------------------------------------------------------------------------
+ek_status ek_run_from_host(ek_handle *h, const double *const in[EK_NFIELDS], int nsteps, double *const out[EK_NFIELDS])
+{
+    if (!h || !in || !out || nsteps < 1) return EK_ERR_INVALID;
+    for (int k = 0; k < EK_NFIELDS; ++k)
+        if (!in[k] || !out[k]) return EK_ERR_INVALID;
+    if (refuse_on_slab(h, "ek_run_from_host")) return EK_ERR_STATE;
+    DeviceGuard g(h->device);
+    ek_status st = ek_alloc_state(h);
+    if (st != EK_OK) return st;
+    const EkConst &c = h->c;
+    const int nblocks = (c.NZ + h->zchunk - 1) / h->zchunk;
+    // plain sequence when there is nothing to pipeline (two-lattice scheme, adopted arrays, one step, tiny grids)
+    bool external = false;
+    for (int k = 0; k < EK_NFIELDS; ++k) external = external || h->fld_external[k];
+    if (h->stream_mode != EK_STREAM_AA || external || nsteps < 2 || nblocks < 4 || h->profile || h->stream == nullptr) {
+        st = ek_set_fields(h, in, 0);
+        if (st == EK_OK) st = ek_init_equilibrium(h);
+        if (st == EK_OK) st = ek_step(h, nsteps);
+        for (int k = 0; k < EK_NFIELDS && st == EK_OK; ++k) st = ek_get_field(h, k, out[k], 0);
+        return st;
+    }
+    if (!h->copy_stream) EK_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    const int G = nblocks < 8 ? nblocks : 8;      // plane groups (multiples of the LBM kernel's z-blocks)
+    while ((int)h->job_events.size() < 2 * G + 2) {
+        cudaEvent_t e;
+        EK_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->job_events.push_back(e);
+    }
+    auto block_of = [&](int gi) { return (int)((long long)nblocks * gi / G); };
+    auto plane_of = [&](int b) { return b * h->zchunk < c.NZ ? b * h->zchunk : c.NZ; };
+    auto copy_planes = [&](int id, int z0, int z1, bool up) -> cudaError_t {
+        const size_t rows = (size_t)c.NY * (z1 - z0);
+        double *dev = h->fld[id] + (size_t)z0 * c.plane;
+        if (up)
+            return cudaMemcpy2DAsync(dev, (size_t)c.PX * sizeof(double), in[id] + (size_t)z0 * c.NY * c.NX,
+                                     (size_t)c.NX * sizeof(double), (size_t)c.NX * sizeof(double), rows,
+                                     cudaMemcpyHostToDevice, h->copy_stream);
+        return cudaMemcpy2DAsync(out[id] + (size_t)z0 * c.NY * c.NX, (size_t)c.NX * sizeof(double), dev,
+                                 (size_t)c.PX * sizeof(double), (size_t)c.NX * sizeof(double), rows, cudaMemcpyDeviceToHost,
+                                 h->copy_stream);
+    };
+    // the copy stream starts after whatever the handle's stream was doing with these arrays
+    EK_CUDA(h, cudaEventRecord(h->job_events[2 * G], h->stream));
+    EK_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->job_events[2 * G], 0));
+    // ---- upload | init_equilibrium | first (even, node-local) LBM pass, group by group
+    h->fields_ready = true;
+    h->pops_ready = true;
+    h->e_from_arrays = true;
+    h->phi_walls_dirty = true;
+    h->efield_stale = false;
+    h->cur = 0;
+    h->parity = 0;
+    h->epoch += 1;
+    StepArgs a = ek_step_args(h);
+    for (int gi = 0; gi < G; ++gi) {
+        const int b0 = block_of(gi), b1 = block_of(gi + 1);
+        const int z0 = plane_of(b0), z1 = plane_of(b1);
+        for (int k = 0; k < EK_NFIELDS; ++k) EK_CUDA(h, copy_planes(k, z0, z1, true));
+        EK_CUDA(h, cudaEventRecord(h->job_events[gi], h->copy_stream));
+        EK_CUDA(h, cudaStreamWaitEvent(h->stream, h->job_events[gi], 0));
+        EK_CUDA(h, ek_launch_init_equilibrium_range(a, h->fld, z0, z1, h->stream));
+        st = ek_stream_collide_save_range(h, 0, b0, b1, gi == G - 1);
+        if (st != EK_OK) return st;
+    }
+    st = ek_fast_poisson(h, 0);
+    if (st != EK_OK) return st;
+    h->steps += 1;
+    // ---- the steps in between
+    if (nsteps > 2) {
+        // (ek_step writes the macroscopic arrays on its last step; harmless here, the final pass rewrites them)
+        st = ek_step(h, nsteps - 2);
+        if (st != EK_OK) return st;
+    }
+    // ---- last LBM pass group by group, rho u c+ c- T downloaded behind it
+    const int lbm_fields[7] = {EK_RHO, EK_UX, EK_UY, EK_UZ, EK_CHARGE, EK_CHARGEN, EK_T};
+    for (int gi = 0; gi < G; ++gi) {
+        const int b0 = block_of(gi), b1 = block_of(gi + 1);
+        st = ek_stream_collide_save_range(h, 1, b0, b1, gi == G - 1);
+        if (st != EK_OK) return st;
+        EK_CUDA(h, cudaEventRecord(h->job_events[G + gi], h->stream));
+        EK_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->job_events[G + gi], 0));
+        for (int k = 0; k < 7; ++k) EK_CUDA(h, copy_planes(lbm_fields[k], plane_of(b0), plane_of(b1), false));
+    }
+    st = ek_fast_poisson(h, 1);
+    if (st != EK_OK) return st;
+    h->steps += 1;
+    EK_CUDA(h, cudaEventRecord(h->job_events[2 * G + 1], h->stream));
+    EK_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->job_events[2 * G + 1], 0));
+    const int poisson_fields[4] = {EK_PHI, EK_EX, EK_EY, EK_EZ};
+    for (int k = 0; k < 4; ++k) EK_CUDA(h, copy_planes(poisson_fields[k], 0, c.NZ, false));
+    EK_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+    EK_CUDA(h, cudaStreamSynchronize(h->stream));
     return EK_OK;
 }
 

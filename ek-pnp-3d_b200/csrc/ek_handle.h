@@ -61,6 +61,10 @@ struct ek_handle {
     long long pair_lbm_launches = 0, pair_poisson_launches = 0;
     long long graph_replays = 0;
 
+    // ek_run_from_host: copy stream and events of the pipelined upload / download
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> job_events;
+
     // counters / profiling
     bool profile = false;
     long long steps = 0, lbm_launches = 0, poisson_launches = 0;

@@ -82,11 +82,13 @@ __device__ __forceinline__ double cidot_literal(int d, double tx, double ty, dou
 // the three scalar sets.
 __global__ void k_init_equilibrium(StepArgs a, const double *r, const double *u, const double *v, const double *w,
                                    const double *ch, const double *chn, const double *T, const double *ex,
-                                   const double *ey, const double *ez, double cs_square, double CFL)
+                                   const double *ey, const double *ez, double cs_square, double CFL, int zfirst)
 {
     const EkConst &c = a.c;
     int x, y, z, i;
     if (!cell_of_thread(c, x, y, z, i)) return;
+    z += zfirst;                       // launch over a range of planes [zfirst, zfirst + gridDim.z)
+    i += (int)(zfirst * c.plane);
     const double ux = u[i], uy = v[i], uz = w[i];
     const double Ex = ex[i], Ey = ey[i], Ez = ez[i];
     const bool wall = (z == 0 || z == c.NZ - 1);
@@ -143,8 +145,16 @@ void ek_launch_pbe_relax(const EkConst &c, double omega, double *phi, double *ph
 
 cudaError_t ek_launch_init_equilibrium(const StepArgs &a, const double *const f[EK_NFIELDS], cudaStream_t st)
 {
+    return ek_launch_init_equilibrium_range(a, f, 0, a.c.NZ, st);
+}
+
+// the planes [z0, z1) only (ek_run_from_host pipelines the upload of the arrays against this kernel)
+cudaError_t ek_launch_init_equilibrium_range(const StepArgs &a, const double *const f[EK_NFIELDS], int z0, int z1,
+                                             cudaStream_t st)
+{
     dim3 b, g = cell_grid(a.c, b);
+    g.z = z1 - z0;
     k_init_equilibrium<<<g, b, 0, st>>>(a, f[EK_RHO], f[EK_UX], f[EK_UY], f[EK_UZ], f[EK_CHARGE], f[EK_CHARGEN],
-                                        f[EK_T], f[EK_EX], f[EK_EY], f[EK_EZ], a.c.cs_square, a.c.CFL);
+                                        f[EK_T], f[EK_EX], f[EK_EY], f[EK_EZ], a.c.cs_square, a.c.CFL, z0);
     return cudaGetLastError();
 }

@@ -205,6 +205,8 @@ cudaError_t ek_launch_step8(const StepArgs &a, int mode, bool write_fields, bool
 cudaError_t ek_launch_export(const StepArgs &a, int mode, int set, double *dst, cudaStream_t st);
 cudaError_t ek_launch_import(const StepArgs &a, int set, const double *src, cudaStream_t st);
 cudaError_t ek_launch_init_equilibrium(const StepArgs &a, const double *const fld[EK_NFIELDS], cudaStream_t st);
+cudaError_t ek_launch_init_equilibrium_range(const StepArgs &a, const double *const fld[EK_NFIELDS], int z0, int z1,
+                                             cudaStream_t st);
 void ek_launch_initialization(const EkConst &c, const ek_params &p, double *const fld[EK_NFIELDS], cudaStream_t st);
 void ek_launch_pbe(const EkConst &c, const ek_params &p, const double *phi, double *charge, double *chargen,
                    double *dq, cudaStream_t st);

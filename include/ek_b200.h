@@ -115,6 +115,14 @@ ek_status ek_step_timed(ek_handle *h, int nsteps, float *ms);
 
 ek_status ek_sync(ek_handle *h);
 
+/* One whole job on HOST arrays (pinned memory recommended), N doubles each in the reference's layout: upload
+ * the eleven arrays (read_data()'s upload, LBM.cu:2629-2671), init_equilibrium() (main.cu:174), nsteps
+ * iterations of main.cu:189-200, download the eleven arrays (the copies of save_data_tecplot,
+ * LBM.cu:2511-2521) -- with the upload pipelined in plane groups against init_equilibrium and the first
+ * LBM pass, and the download of rho, u, c+, c-, T against the last LBM pass.  Blocking; same results as
+ * ek_set_fields + ek_init_equilibrium + ek_step + ek_get_field, bit for bit. */
+ek_status ek_run_from_host(ek_handle *h, const double *const in[EK_NFIELDS], int nsteps, double *const out[EK_NFIELDS]);
+
 /* Replaces the cudaMemcpy D2H calls of save_data_tecplot/current/record_umax
  * (LBM.cu:2511-2521, main.cu:212-214, LBM.cu:2720-2722). */
 ek_status ek_get_field(ek_handle *h, int id, double *dst, int dst_on_device);

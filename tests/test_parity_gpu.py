@@ -265,6 +265,34 @@ def test_step_graph_is_bitwise_identical(ek):
         assert np.array_equal(p, base_p), key
 
 
+@pytest.mark.parametrize("nsteps", [1, 2, 3, 6])
+def test_run_from_host_is_bitwise_identical_to_the_plain_sequence(ek, nsteps):
+    """ek_run_from_host (upload, init_equilibrium, n steps, download as ONE call with the PCIe copies
+    pipelined against the first and last LBM pass) against set_fields + init_equilibrium + step + fields"""
+    over = dict(NX=40, NY=6, NZ=37, uw=1.0e-4, exf=1.0e6, voltage2=-3.0e-3)
+    init = synthetic_init(over)
+    sim = ek.Simulation(ek.default_params(**over), zchunk=4)
+    sim.set_fields(init)
+    sim.init_equilibrium()
+    sim.step(nsteps)
+    want = sim.fields()
+    wantP = np.stack([sim.populations(s) for s in range(4)])
+    sim.close()
+    sim = ek.Simulation(ek.default_params(**over), zchunk=4)
+    got = sim.run_from_host(init, nsteps)
+    gotP = np.stack([sim.populations(s) for s in range(4)])
+    assert sim.counter("steps") == nsteps
+    for k in util.FIELDS:
+        assert np.array_equal(got[k], want[k]), k
+    assert np.array_equal(gotP, wantP)
+    # and again on the used handle, into caller-provided arrays
+    out = {k: np.empty_like(want[k]) for k in util.FIELDS}
+    sim.run_from_host(init, nsteps, out)
+    for k in util.FIELDS:
+        assert np.array_equal(out[k], want[k]), k
+    sim.close()
+
+
 def test_state_machine_errors(ek):
     sim = ek.Simulation(ek.default_params(NX=8, NY=2, NZ=7))
     with pytest.raises(ek.EkError):
