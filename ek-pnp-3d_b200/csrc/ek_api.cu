@@ -1,7 +1,11 @@
 // ek_api.cu -- the C ABI of include/ek_b200.h: handle life cycle, start-up,
 // the coupled step loop (main.cu:189-200 of the reference) and accessors.
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <chrono>
 
 #include <vector>
 
@@ -686,6 +690,18 @@ ek_status ek_run_from_host(ek_handle *h, const double *const in[EK_NFIELDS], int
                                  (size_t)c.PX * sizeof(double), (size_t)c.NX * sizeof(double), rows, cudaMemcpyDeviceToHost,
                                  h->copy_stream);
     };
+    // EK_JOB_DEBUG=1: synchronise after every phase and print its wall time (development aid)
+    const bool dbg = getenv("EK_JOB_DEBUG") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_prev = now();
+    auto phase = [&](const char *name) {
+        if (!dbg) return;
+        cudaStreamSynchronize(h->copy_stream);
+        cudaStreamSynchronize(h->stream);
+        const double t = now();
+        fprintf(stderr, "ek_run_from_host: %-28s %8.3f ms\n", name, t - t_prev);
+        t_prev = t;
+    };
     // the copy stream starts after whatever the handle's stream was doing with these arrays
     EK_CUDA(h, cudaEventRecord(h->job_events[2 * G], h->stream));
     EK_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->job_events[2 * G], 0));
@@ -709,15 +725,18 @@ ek_status ek_run_from_host(ek_handle *h, const double *const in[EK_NFIELDS], int
         st = ek_stream_collide_save_range(h, 0, b0, b1, gi == G - 1);
         if (st != EK_OK) return st;
     }
+    phase("upload+init+first LBM pass");
     st = ek_fast_poisson(h, 0);
     if (st != EK_OK) return st;
     h->steps += 1;
+    phase("first Poisson solve");
     // ---- the steps in between
     if (nsteps > 2) {
         // (ek_step writes the macroscopic arrays on its last step; harmless here, the final pass rewrites them)
         st = ek_step(h, nsteps - 2);
         if (st != EK_OK) return st;
     }
+    phase("steps in between");
     // ---- last LBM pass group by group, rho u c+ c- T downloaded behind it
     const int lbm_fields[7] = {EK_RHO, EK_UX, EK_UY, EK_UZ, EK_CHARGE, EK_CHARGEN, EK_T};
     for (int gi = 0; gi < G; ++gi) {
@@ -728,6 +747,7 @@ ek_status ek_run_from_host(ek_handle *h, const double *const in[EK_NFIELDS], int
         EK_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->job_events[G + gi], 0));
         for (int k = 0; k < 7; ++k) EK_CUDA(h, copy_planes(lbm_fields[k], plane_of(b0), plane_of(b1), false));
     }
+    phase("last LBM pass + 7 downloads");
     st = ek_fast_poisson(h, 1);
     if (st != EK_OK) return st;
     h->steps += 1;
@@ -737,6 +757,7 @@ ek_status ek_run_from_host(ek_handle *h, const double *const in[EK_NFIELDS], int
     for (int k = 0; k < 4; ++k) EK_CUDA(h, copy_planes(poisson_fields[k], 0, c.NZ, false));
     EK_CUDA(h, cudaStreamSynchronize(h->copy_stream));
     EK_CUDA(h, cudaStreamSynchronize(h->stream));
+    phase("last solve + 4 downloads");
     return EK_OK;
 }
 
