@@ -191,7 +191,7 @@ def run_reference(args, rank: int):
         return
     v = round(best["mlups"], 2)
     extra = {}
-    if not args.no_extra:
+    if not args.no_extra and args.gpus == 1:      # once per round is enough: the N > 1 launches skip it
         import re
         import tempfile
         for name, steps2 in (("c1", 1000), ("c2", 200)):     # step-only, CUDA events around main.cu:192-198
@@ -329,7 +329,7 @@ def bench_ranks(ek, dist, torch, args, w, local_rank):
             cells4 = c4w["NX"] * c4w["NY"] * c4w["NZ"]
             steps4 = max(args.steps, 40)
             tried = {}
-            for K4 in (2, 4):       # at 8.4 M cells per GPU the pipeline depth is a launch-count trade-off: report both
+            for K4 in (1, 2, 4):    # at 8.4 M cells per GPU the pipeline depth is a launch-count trade-off: report all
                 r4 = ek.RankSimulation(p4, local_rank, rank, world, bcast, poisson_chunks=K4)
                 r4.init()
                 tried[K4] = _timed_ranks(r4, dist, torch, steps4, max(args.warmup, 10))

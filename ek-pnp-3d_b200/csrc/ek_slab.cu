@@ -24,28 +24,42 @@ __constant__ int kMinus[9] = {2, 8, 10, 14, 16, 20, 22, 24, 25};  // c_x = -1
 
 struct Lat4 { double *p[4]; };
 
-// buf[((s*9 + k)*NZ + z)*NY + y]  <->  slot list[k] of column `col` of set s
+// buf[((s*9 + k)*NZ + z)*NY + y]  <->  slot list[k] of column `col` of set s.  One launch serves both faces of
+// the slab (blockIdx.z = face*36 + s*9 + k): half the launches of a halo exchange, which at 8 M cells per GPU is
+// latency, not bandwidth
+struct HaloFaces {
+    int col[2], plus[2];
+    double *buf[2];
+};
+
 template <bool PACK>
-__global__ void k_halo_column(EkConst c, Lat4 lat, int col, int plus, double *buf)
+__global__ void k_halo_column(EkConst c, Lat4 lat, HaloFaces f)
 {
     const int y = blockIdx.x * blockDim.x + threadIdx.x;
     if (y >= c.NY) return;
     const int z = blockIdx.y;
-    const int s = blockIdx.z / 9, k = blockIdx.z % 9;
-    const int d = plus ? kPlus[k] : kMinus[k];
-    double *q = lat.p[s] + (size_t)z * c.lplane + (size_t)y * c.lrow + ek_lat_col(col) + (size_t)d * EK_TILE;
-    double *b = buf + (((size_t)(s * 9 + k) * c.NZ + z) * c.NY + y);
+    const int face = blockIdx.z / 36, sk = blockIdx.z % 36;
+    const int s = sk / 9, k = sk % 9;
+    const int d = f.plus[face] ? kPlus[k] : kMinus[k];
+    double *q = lat.p[s] + (size_t)z * c.lplane + (size_t)y * c.lrow + ek_lat_col(f.col[face]) + (size_t)d * EK_TILE;
+    double *b = f.buf[face] + (((size_t)(s * 9 + k) * c.NZ + z) * c.NY + y);
     if (PACK) *b = *q; else *q = *b;
 }
 
+struct PhiFaces {
+    int col[2];
+    double *buf[2];
+};
+
 template <bool PACK>
-__global__ void k_phi_column(EkConst c, double *phi, int col, double *buf, int z0)
+__global__ void k_phi_column(EkConst c, double *phi, PhiFaces f, int z0)
 {
     const int y = blockIdx.x * blockDim.x + threadIdx.x;
     if (y >= c.NY) return;
     const int z = z0 + blockIdx.y;
-    double *q = phi + (size_t)z * c.plane + (size_t)y * c.PX + col;
-    double *b = buf + (size_t)z * c.NY + y;
+    const int face = blockIdx.z;
+    double *q = phi + (size_t)z * c.plane + (size_t)y * c.PX + f.col[face];
+    double *b = f.buf[face] + (size_t)z * c.NY + y;
     if (PACK) *b = *q; else *q = *b;
 }
 
@@ -112,15 +126,18 @@ ek_status ek_halo_pack(ek_handle *h, int phase, double *to_left, double *to_righ
     if (!h || !h->slab || !h->pops_ready) return EK_ERR_STATE;
     DeviceGuard g(h->device);
     const EkConst &c = h->c;
-    dim3 b(128), gr((c.NY + 127) / 128, c.NZ, 36);
+    dim3 b(128), gr((c.NY + 127) / 128, c.NZ, 72);
     Lat4 l = current_lattice(h);
+    HaloFaces f;
+    f.buf[0] = to_right; f.buf[1] = to_left;
     if (phase == 0) {
-        k_halo_column<true><<<gr, b, 0, h->stream>>>(c, l, c.NX - 1, 0, to_right);  // last column, c_x = -1 slots
-        k_halo_column<true><<<gr, b, 0, h->stream>>>(c, l, 0, 1, to_left);          // first column, c_x = +1 slots
+        f.col[0] = c.NX - 1; f.plus[0] = 0;   // last column, c_x = -1 slots
+        f.col[1] = 0;        f.plus[1] = 1;   // first column, c_x = +1 slots
     } else {
-        k_halo_column<true><<<gr, b, 0, h->stream>>>(c, l, c.xhi, 1, to_right);     // right ghost, c_x = +1 slots
-        k_halo_column<true><<<gr, b, 0, h->stream>>>(c, l, c.xlo, 0, to_left);      // left ghost, c_x = -1 slots
+        f.col[0] = c.xhi;    f.plus[0] = 1;   // right ghost, c_x = +1 slots
+        f.col[1] = c.xlo;    f.plus[1] = 0;   // left ghost, c_x = -1 slots
     }
+    k_halo_column<true><<<gr, b, 0, h->stream>>>(c, l, f);
     EK_CUDA(h, cudaGetLastError());
     return EK_OK;
 }
@@ -130,15 +147,18 @@ ek_status ek_halo_unpack(ek_handle *h, int phase, const double *from_left, const
     if (!h || !h->slab || !h->pops_ready) return EK_ERR_STATE;
     DeviceGuard g(h->device);
     const EkConst &c = h->c;
-    dim3 b(128), gr((c.NY + 127) / 128, c.NZ, 36);
+    dim3 b(128), gr((c.NY + 127) / 128, c.NZ, 72);
     Lat4 l = current_lattice(h);
+    HaloFaces f;
+    f.buf[0] = const_cast<double *>(from_left); f.buf[1] = const_cast<double *>(from_right);
     if (phase == 0) {
-        k_halo_column<false><<<gr, b, 0, h->stream>>>(c, l, c.xlo, 0, const_cast<double *>(from_left));
-        k_halo_column<false><<<gr, b, 0, h->stream>>>(c, l, c.xhi, 1, const_cast<double *>(from_right));
+        f.col[0] = c.xlo; f.plus[0] = 0;
+        f.col[1] = c.xhi; f.plus[1] = 1;
     } else {
-        k_halo_column<false><<<gr, b, 0, h->stream>>>(c, l, 0, 1, const_cast<double *>(from_left));
-        k_halo_column<false><<<gr, b, 0, h->stream>>>(c, l, c.NX - 1, 0, const_cast<double *>(from_right));
+        f.col[0] = 0;        f.plus[0] = 1;
+        f.col[1] = c.NX - 1; f.plus[1] = 0;
     }
+    k_halo_column<false><<<gr, b, 0, h->stream>>>(c, l, f);
     EK_CUDA(h, cudaGetLastError());
     return EK_OK;
 }
@@ -151,9 +171,11 @@ ek_status ek_phi_halo_pack_range(ek_handle *h, int z0, int z1, double *to_left, 
     if (z0 < 0 || z1 > h->c.NZ || z1 <= z0) return EK_ERR_INVALID;
     DeviceGuard g(h->device);
     const EkConst &c = h->c;
-    dim3 b(128), gr((c.NY + 127) / 128, z1 - z0);
-    k_phi_column<true><<<gr, b, 0, h->stream>>>(c, h->fld[EK_PHI], 0, to_left, z0);
-    k_phi_column<true><<<gr, b, 0, h->stream>>>(c, h->fld[EK_PHI], c.NX - 1, to_right, z0);
+    dim3 b(128), gr((c.NY + 127) / 128, z1 - z0, 2);
+    PhiFaces f;
+    f.col[0] = 0; f.buf[0] = to_left;
+    f.col[1] = c.NX - 1; f.buf[1] = to_right;
+    k_phi_column<true><<<gr, b, 0, h->stream>>>(c, h->fld[EK_PHI], f, z0);
     EK_CUDA(h, cudaGetLastError());
     return EK_OK;
 }
@@ -164,9 +186,11 @@ ek_status ek_phi_halo_unpack_range(ek_handle *h, int z0, int z1, const double *f
     if (z0 < 0 || z1 > h->c.NZ || z1 <= z0) return EK_ERR_INVALID;
     DeviceGuard g(h->device);
     const EkConst &c = h->c;
-    dim3 b(128), gr((c.NY + 127) / 128, z1 - z0);
-    k_phi_column<false><<<gr, b, 0, h->stream>>>(c, h->fld[EK_PHI], c.xlo, const_cast<double *>(from_left), z0);
-    k_phi_column<false><<<gr, b, 0, h->stream>>>(c, h->fld[EK_PHI], c.xhi, const_cast<double *>(from_right), z0);
+    dim3 b(128), gr((c.NY + 127) / 128, z1 - z0, 2);
+    PhiFaces f;
+    f.col[0] = c.xlo; f.buf[0] = const_cast<double *>(from_left);
+    f.col[1] = c.xhi; f.buf[1] = const_cast<double *>(from_right);
+    k_phi_column<false><<<gr, b, 0, h->stream>>>(c, h->fld[EK_PHI], f, z0);
     EK_CUDA(h, cudaGetLastError());
     return EK_OK;
 }
