@@ -329,12 +329,12 @@ def bench_ranks(ek, dist, torch, args, w, local_rank):
             cells4 = c4w["NX"] * c4w["NY"] * c4w["NZ"]
             steps4 = max(args.steps, 40)
             tried = {}
-            for K4 in (1, 2, 4):    # at 8.4 M cells per GPU the pipeline depth is a launch-count trade-off: report all
+            for K4 in (1, 2, 4, 0):  # at 8.4 M cells per GPU the pipeline depth is a launch-count trade-off: report all (0 = automatic)
                 r4 = ek.RankSimulation(p4, local_rank, rank, world, bcast, poisson_chunks=K4)
                 r4.init()
                 tried[K4] = _timed_ranks(r4, dist, torch, steps4, max(args.warmup, 10))
-                if K4 == 4:
-                    ph4 = r4.profile(4, False)
+                if K4 == 0:
+                    ph4 = {"pipelined_main_stream": r4.profile(4, False), "sequential_no_overlap": r4.profile(4, True)}
                 r4.close()
             K4 = min(tried, key=tried.get)
             ms4 = tried[K4]
@@ -349,7 +349,7 @@ def bench_ranks(ek, dist, torch, args, w, local_rank):
             ms1 = float(one.item())
             c4 = {"workload": c4w["name"], "n_gpus": world, "steps": steps4, "poisson_chunks": K4,
                   "ms_per_step_by_chunks": {str(k): round(v / steps4, 4) for k, v in tried.items()},
-                  "phase_ms_rank0_4_chunks": ph4, "ms_per_step": round(ms4 / steps4, 4),
+                  "phase_ms_rank0_auto_chunks": ph4, "ms_per_step": round(ms4 / steps4, 4),
                   "mlups": round(cells4 * steps4 / (ms4 * 1e-3) / 1e6, 1),
                   "one_gpu_ms_per_step": round(ms1 / steps4, 4), "one_gpu_mlups": round(cells4 * steps4 / (ms1 * 1e-3) / 1e6, 1),
                   "speedup": round(ms1 / ms4, 3), "efficiency_vs_one_gpu": round(ms1 / ms4 / world, 4),
@@ -393,7 +393,8 @@ def main():
     ap.add_argument("--kernel", type=int, default=None, help="LBM kernel variant (ek_set_option kernel)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the C1 / C2 records of the `extra` key")
-    ap.add_argument("--poisson-chunks", type=int, default=4, help="N>1: z-chunks of the distributed Poisson stage")
+    ap.add_argument("--poisson-chunks", type=int, default=0,
+                    help="N>1: z-chunks of the distributed Poisson stage (0: automatic, 7 chunks of sizes 1:2:3:4:3:2:1)")
     ap.add_argument("--transport", default="nccl", choices=["nccl", "p2p", "dma"],
                     help="N>1: Poisson transposes by NCCL all-to-all or by direct peer-memory writes (CUDA IPC)")
     ap.add_argument("--driver", default="native", choices=["native", "python"],

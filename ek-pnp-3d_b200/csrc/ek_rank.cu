@@ -395,7 +395,7 @@ ek_status ek_rank_create(const ek_params *global, int device, int rank, int nran
             if (n != ncclSuccess) return fail(EK_ERR_CUDA, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(n));
         }
     }
-    st = ek_slab_poisson_setup(r->h, poisson_chunks > 0 ? poisson_chunks : 4);
+    st = ek_slab_poisson_setup(r->h, poisson_chunks);   // <= 0: automatic chunk sizes
     if (st != EK_OK) return fail(st, ek_last_error(r->h));
     r->K = ek_slab_poisson_chunks(r->h);
     bool ok = true;

@@ -248,7 +248,7 @@ ek_status ek_compute_efield(ek_handle *h);
  *     scatter_x(k); all-to-all(send_k -> recv_k); backward(k)
  * and ek_poisson_finish().  send/recv hold `count` complex doubles in nranks
  * equal parts (part i travels to / comes from rank i). */
-ek_status ek_slab_poisson_setup(ek_handle *h, int nchunks);
+ek_status ek_slab_poisson_setup(ek_handle *h, int nchunks);   /* nchunks <= 0: automatic (7 chunks 1:2:3:4:3:2:1 of the z-blocks, or 4 equal ones) */
 int ek_slab_poisson_chunks(ek_handle *h);
 ek_status ek_slab_poisson_chunk(ek_handle *h, int k, int *block0, int *block1, void **send, void **recv,
                                 long long *count);
