@@ -132,6 +132,10 @@ def load_library(path: str | None = None):
                  "ek_slab_poisson_backward", "ek_slab_poisson_push_x", "ek_slab_poisson_push_back"):
         getattr(L, name).argtypes = [H, C.c_int]
     L.ek_slab_poisson_solve.argtypes = [H]
+    L.ek_slab_poisson_enable_ghosts.argtypes = [H]
+    L.ek_slab_poisson_chunk_back.argtypes = [H, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_longlong)]
+    L.ek_slab_poisson_scatter_xg.argtypes = [H, C.c_int]
+    L.ek_slab_poisson_backward_g.argtypes = [H, C.c_int]
     L.ek_adopt_field.argtypes = [H, C.c_int, C.c_void_p]
     L.ek_wall_current.argtypes = [H, C.POINTER(C.c_double)]
     L.ek_max_uz.argtypes = [H, C.POINTER(C.c_double)]

@@ -188,6 +188,11 @@ struct EkSlabPoisson {
     cufftDoubleComplex *peerR[EK_MAX_RANKS] = {};
     bool peer_ipc[EK_MAX_RANKS] = {};              // mapped through CUDA IPC (to be closed)
     bool dma = false;                              // pushes by strided copies on the copy engines
+    // way back with the two ghost columns of phi travelling inside transpose 2 (ek_slab_poisson_enable_ghosts):
+    // rows of NXl + 2 columns [my columns, right neighbour's first, left neighbour's last]
+    bool ghosts = false;
+    cufftDoubleComplex *Sg = nullptr, *Rg = nullptr;   // [P*kyl][M][NXl+2] per chunk, as S / R
+    std::map<int, cufftHandle> plan_ybg;               // inverse y-transforms of NXl+2 columns per chunk height
 };
 void ek_slab_poisson_destroy(ek_handle *h);
 

@@ -198,7 +198,8 @@ __global__ void __launch_bounds__(EK_ZSOLVE_BLOCK) k_zsolve(int nreal, int ncols
 __global__ void k_set_walls(EkConst c, double *__restrict__ phi)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= c.NX) return;
+    // every column of the row, ghost columns of a slab included (the neighbours' wall values are the same constants)
+    if (x >= c.PX) return;
     const int y = blockIdx.y;
     const size_t top = (size_t)(c.NZ - 1) * c.plane;
     phi[(size_t)y * c.PX + x] = c.voltage;          // poisson.cu:195-197
@@ -308,7 +309,7 @@ void ek_launch_zsolve_rows(int rows, int NXg, int M, double *x, const double *cp
 
 void ek_launch_set_walls(const EkConst &c, double *phi, cudaStream_t st)
 {
-    k_set_walls<<<dim3((c.NX + 127) / 128, c.NY), 128, 0, st>>>(c, phi);
+    k_set_walls<<<dim3((c.PX + 127) / 128, c.NY), 128, 0, st>>>(c, phi);
 }
 
 void ek_launch_efield(const EkConst &c, const double *phi, double *Ex, double *Ey, double *Ez, cudaStream_t st)
@@ -374,7 +375,7 @@ ek_status ek_poisson_solve(ek_handle *h, EkPoisson &P, const ek_params &p, const
         // the transforms never touch the wall planes: re-impose them only when something else wrote phi
         // (start-up relaxation, uploads; poisson.cu:195-201 does it on every call)
         if (h->phi_walls_dirty || h->fld_external[EK_PHI]) {   // an adopted array may be written by its owner
-            k_set_walls<<<dim3((c.NX + 127) / 128, c.NY), b, 0, st>>>(c, phi);
+            k_set_walls<<<dim3((c.PX + 127) / 128, c.NY), b, 0, st>>>(c, phi);
             h->phi_walls_dirty = false;
             n = 2;
         }

@@ -73,6 +73,7 @@ struct ek_rank {
     cudaEvent_t ev_side = nullptr, ev_main = nullptr, ev_halo = nullptr, ev_back = nullptr, ev_bnd = nullptr;
     bool have_phi_ready = false;
     bool overlap = true, overlap_back = true;
+    bool ghosts = true;           // phi ghost columns inside transpose 2 (ek_slab_poisson_enable_ghosts)
     // LBM pass: boundary x-tiles first, population halos under the interior launches.  Measured at 2 x 134 M cells:
     // the split pass costs 1.4 ms more than it hides (halos are hidden behind the Poisson stage anyway): off by default
     bool boundary_first = false;
@@ -164,11 +165,12 @@ ek_status ring_exchange(ek_rank *r, int which, const double *to_l, const double 
 }
 
 // all-to-all of the transpose buffers of chunk k: part i of `send` travels to rank i
-ek_status all_to_all(ek_rank *r, int k, cudaStream_t st)
+ek_status all_to_all(ek_rank *r, int k, cudaStream_t st, bool back = false)
 {
     void *send = nullptr, *recv = nullptr;
     long long count = 0;
-    RK(r, ek_slab_poisson_chunk(r->h, k, nullptr, nullptr, &send, &recv, &count));
+    if (back && r->ghosts) RK(r, ek_slab_poisson_chunk_back(r->h, k, &send, &recv, &count));
+    else RK(r, ek_slab_poisson_chunk(r->h, k, nullptr, nullptr, &send, &recv, &count));
     if (count == 0) return EK_OK;
     const size_t n = (size_t)(count / r->P) * 2;   // doubles per part (complex)
     if (r->P == 1) {
@@ -216,10 +218,10 @@ ek_status poisson_tail(ek_rank *r)
     RK(r, ek_poisson_finish(h, 0));   // wall planes first (only when something other than the solver wrote phi)
     for (int k = 0; k < r->K; ++k) {
         RCUDA(r, cudaStreamWaitEvent(r->back, r->ev_landed[k], 0));
-        RK(r, ek_slab_poisson_backward(h, k));
+        RK(r, r->ghosts ? ek_slab_poisson_backward_g(h, k) : ek_slab_poisson_backward(h, k));
         int z0, z1;
         chunk_planes(r, k, &z0, &z1);
-        if (z1 > z0) {
+        if (z1 > z0 && !r->ghosts) {
             RK(r, ek_phi_halo_pack_range(h, z0, z1, r->pto_l, r->pto_r));
             const size_t a = (size_t)z0 * h->c.NY, n = (size_t)(z1 - z0) * h->c.NY;
             RK(r, ring_exchange(r, COMM_P, r->pto_l + a, r->pto_r + a, r->pfrom_l + a, r->pfrom_r + a, n, r->back));
@@ -247,10 +249,10 @@ ek_status poisson_rest(ek_rank *r, cudaStream_t fwd)
     RK(r, ek_slab_poisson_solve(h));
     RK(r, mark(r, "x_fft_zsolve_x_ifft"));
     for (int k = 0; k < r->K; ++k) {
-        RK(r, ek_slab_poisson_scatter_x(h, k));
+        RK(r, r->ghosts ? ek_slab_poisson_scatter_xg(h, k) : ek_slab_poisson_scatter_x(h, k));
         RCUDA(r, cudaEventRecord(r->ev_sc[k], h->stream));
         RCUDA(r, cudaStreamWaitEvent(r->copy, r->ev_sc[k], 0));
-        RK(r, all_to_all(r, k, r->copy));          // chunk k travels while chunk k+1 is re-blocked
+        RK(r, all_to_all(r, k, r->copy, true));    // chunk k travels while chunk k+1 is re-blocked
         RCUDA(r, cudaEventRecord(r->ev_landed[k], r->copy));
     }
     RK(r, mark(r, "scatter_x"));
@@ -398,6 +400,11 @@ ek_status ek_rank_create(const ek_params *global, int device, int rank, int nran
     st = ek_slab_poisson_setup(r->h, poisson_chunks);   // <= 0: automatic chunk sizes
     if (st != EK_OK) return fail(st, ek_last_error(r->h));
     r->K = ek_slab_poisson_chunks(r->h);
+    if (const char *gh = getenv("EK_RANK_GHOSTS")) r->ghosts = atoi(gh) != 0;
+    if (r->ghosts) {
+        st = ek_slab_poisson_enable_ghosts(r->h);
+        if (st != EK_OK) return fail(st, ek_last_error(r->h));
+    }
     bool ok = true;
     // The side streams run at the HIGHEST priority: an LBM launch keeps every SM full for milliseconds, and at
     // equal priority the transforms / NCCL kernels queued next to it only get thread-block slots when the LBM

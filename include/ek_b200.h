@@ -257,6 +257,12 @@ ek_status ek_slab_poisson_gather_x(ek_handle *h, int k);
 ek_status ek_slab_poisson_solve(ek_handle *h);
 ek_status ek_slab_poisson_scatter_x(ek_handle *h, int k);
 ek_status ek_slab_poisson_backward(ek_handle *h, int k);
+/* Way back with the two ghost columns of phi travelling inside transpose 2 (no separate phi halo exchange):
+ * after enable_ghosts the host runs scatter_xg(k); all-to-all(chunk_back buffers); backward_g(k) per chunk */
+ek_status ek_slab_poisson_enable_ghosts(ek_handle *h);
+ek_status ek_slab_poisson_chunk_back(ek_handle *h, int k, void **send, void **recv, long long *count);
+ek_status ek_slab_poisson_scatter_xg(ek_handle *h, int k);
+ek_status ek_slab_poisson_backward_g(ek_handle *h, int k);
 /* Direct peer-memory transport of the two transposes (one node, NVLink): every
  * rank maps the pencil and receive buffers of every other rank -- CUDA IPC
  * handles exported here and exchanged by the host (ipc_bytes() bytes per rank),
