@@ -213,6 +213,9 @@ __device__ __forceinline__ void gather27_lean(const LeanAddr &la, double S[27])
 // latency bound at 16 warps per SM, its loads in flight are limited by registers, a prefetch is not.
 // Next iteration's planes z, z+1 are this iteration's b[1], b[2] (addresses already formed, other slots);
 // only plane z+2 needs new addresses.
+#ifndef EK_PF_INSTR
+#define EK_PF_INSTR "prefetch.global.L2"
+#endif
 __device__ __forceinline__ void prefetch27_lean_odd(const LeanAddr &la, unsigned lplane)
 {
 #pragma unroll
@@ -220,7 +223,7 @@ __device__ __forceinline__ void prefetch27_lean_odd(const LeanAddr &la, unsigned
         const int k = 1 - ek_cz(d);
         double *base = k == 2 ? la.b[2] + lplane : la.b[k + 1];
         const double *q = lean_ptr(base, la.oxy[1 - ek_cy(d)][1 - ek_cx(d)]) + ek_opp(d) * EK_TILE;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+        asm volatile(EK_PF_INSTR " [%0];" ::"l"(q));
     }
 }
 

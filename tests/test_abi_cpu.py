@@ -77,3 +77,22 @@ def test_product_does_not_reference_the_oracle():
                 with open(os.path.join(dirpath, fn)) as f:
                     txt = f.read()
                 assert "ek_oracle" not in txt and "import oracle" not in txt and "from oracle" not in txt, fn
+
+
+def test_shim_exports_the_reference_signatures():
+    """libek_b200_shim.so: the four hot-path functions of the reference with their C++ signatures
+    (LBM.h:159-176), the globals fast_Poisson writes as WEAK references (resolved against main.cu when it
+    is linked in), and the configuration hooks"""
+    import subprocess
+    so = os.path.join(util.ROOT, "ek-pnp-3d_b200", "libek_b200_shim.so")
+    out = subprocess.run(["nm", "-D", "-C", so], capture_output=True, text=True, check=True).stdout
+    ptr = "double*"
+    for sig in ("initialization(" + ", ".join([ptr] * 11) + ")",
+                "init_equilibrium(" + ", ".join([ptr] * 18) + ")",
+                "stream_collide_save(" + ", ".join([ptr] * 22) + ", double, double*)",
+                "fast_Poisson(" + ", ".join([ptr] * 5) + ", int)"):
+        assert any(l.split(" ", 2)[-1] == sig and " T " in l for l in out.splitlines()), sig
+    for g in ("phi_gpu", "Ex_gpu", "Ey_gpu", "Ez_gpu"):
+        assert any(l.strip().endswith(" " + g) and " w " in l for l in out.splitlines()), g
+    for f in ("ek_shim_configure", "ek_shim_bind_potential", "ek_shim_handle"):
+        assert f" T {f}" in out, f

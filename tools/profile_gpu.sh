@@ -6,7 +6,7 @@
 # Outputs land in gpurun_out/; tools/ncu_summary.py turns them into profiles/*.json|csv.
 set -u
 TAG=${1:-r01b}
-CMD="python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-e2e --pb-iters 20"
+CMD="python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-e2e --no-extra --pb-iters 20"
 mkdir -p gpurun_out
 $CMD > gpurun_out/${TAG}_plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/${TAG}_plain.log; exit 1; }
 tail -1 gpurun_out/${TAG}_plain.log
