@@ -186,6 +186,7 @@ StepArgs ek_step_args(ek_handle *h)
     a.fld[0] = h->fld[EK_RHO]; a.fld[1] = h->fld[EK_UX]; a.fld[2] = h->fld[EK_UY]; a.fld[3] = h->fld[EK_UZ];
     a.fld[4] = h->fld[EK_CHARGE]; a.fld[5] = h->fld[EK_CHARGEN]; a.fld[6] = h->fld[EK_T];
     a.zchunk = h->zchunk;
+    a.row_imm = h->kernel == 0 ? 1 : 0;   // kernel 4: the generic lean kernel for the odd step too (A/B partner)
     return a;
 }
 
@@ -313,7 +314,7 @@ ek_status ek_set_option(ek_handle *h, const char *key, long long value)
         // 3: four warps, general path everywhere (cross-check of the lean path)
         // 5: x-marching rows with sector-aligned stores for the odd A-A step (measured slower than the
         // z-walking default; kept selectable for the A/B profile)
-        if (value < 0 || value > 6 || value == 4) return EK_ERR_INVALID;   // 6: marching with aligned loads too
+        if (value < 0 || value > 6) return EK_ERR_INVALID;   // 4: generic lean kernel (no row-stride immediates); 5/6: marching
 #ifndef EK_XCHECK
         if (value == 1 || value == 2 || value >= 5) { ek_set_error(h, "kernel variants 1, 2, 5, 6 are only in the cross-check build libek_b200_xcheck.so"); return EK_ERR_INVALID; }
 #endif
@@ -500,7 +501,7 @@ ek_status ek_stream_collide_save_part(ek_handle *h, int write_fields, int zblock
     StepArgs a = ek_step_args(h);
     a.zblock0 = zblock0;
     a.nzblocks = zblock1 > 0 ? zblock1 - zblock0 : 0;
-    if (xtiles < 0 || xtiles > 2 || (xtiles != 0 && h->kernel != 0 && h->kernel != 3)) return EK_ERR_INVALID;
+    if (xtiles < 0 || xtiles > 2 || (xtiles != 0 && h->kernel != 0 && h->kernel != 3 && h->kernel != 4)) return EK_ERR_INVALID;
     a.xt_mode = xtiles;
     const int mode = h->stream_mode == EK_STREAM_PUSH ? EK_MODE_PUSH : (h->parity ? EK_MODE_AA_ODD : EK_MODE_AA_EVEN);
     cudaEvent_t e0 = nullptr, e1 = nullptr;

@@ -102,6 +102,7 @@ struct StepArgs {
     double *fld[7];       // rho ux uy uz charge chargen T (only when fields are written)
     int zchunk;
     int zblock0, nzblocks;  // sub-range of z-chunks for this launch (nzblocks = 0: all)
+    int row_imm;            // 1: odd lean launches may take the kernel with the row stride as an immediate
     int xt_mode;            // x-tiles of this launch: 0 all, 1 the two boundary tiles of the row (0 and last), 2 the interior ones
     // x-marching launch of the odd A-A step (ek_march_kernel): deep-interior planes [march_z0, march_z0 +
     // march_planes) walk their x-rows; the wall-adjacent plane ranges take the general node path

@@ -68,7 +68,7 @@ __device__ __forceinline__ void scalar_pair_trt(const double S[27], const double
     Ob = b - (np_ - nm_);
 }
 
-template <int MODE, bool LEAN, int p>
+template <int MODE, bool LEAN, int p, int LROW = 0>
 struct ScalarPairs {
     // TRT relaxation of the opposite pair (d, d+1), d = 2p+1 (LBM.cu:1148-1845),
     // then delivery of both results.
@@ -82,8 +82,8 @@ struct ScalarPairs {
         scalar_pair_trt<d>(S, wcm, omusq, vtx, vty, vtz, wp, wmn, Oa, Ob);
         if (act) {
             if (LEAN) {
-                putx<MODE, d, true>(lout, nb, la, Oa);
-                putx<MODE, o, true>(lout, nb, la, Ob);
+                putx<MODE, d, true, LROW>(lout, nb, la, Oa);
+                putx<MODE, o, true, LROW>(lout, nb, la, Ob);
             } else if (!wall) {
                 if (MODE == EK_MODE_AA_EVEN) {
                     put<MODE, d>(lout, nb, Oa);
@@ -118,19 +118,19 @@ struct ScalarPairs {
                 }
             }
         }
-        ScalarPairs<MODE, LEAN, p + 1>::run(S, wcm, omusq, vtx, vty, vtz, wp, wmn, wall, bottom, is_temp, c, lout, nb, la,
-                                            z, Wn, act);
+        ScalarPairs<MODE, LEAN, p + 1, LROW>::run(S, wcm, omusq, vtx, vty, vtz, wp, wmn, wall, bottom, is_temp, c, lout, nb,
+                                                  la, z, Wn, act);
     }
 };
-template <int MODE, bool LEAN>
-struct ScalarPairs<MODE, LEAN, 13> {
+template <int MODE, bool LEAN, int LROW>
+struct ScalarPairs<MODE, LEAN, 13, LROW> {
     static __device__ __forceinline__ void run(const double *, double *, double, double, double, double, double, double,
                                                bool, bool, bool, const EkConst &, double *, const Nbr &,
                                                const LeanAddr &, int, double *, bool) {}
 };
 
 // one node of a scalar set.  LEAN: deep interior (2 <= z <= NZ-3), see LeanAddr.
-template <int MODE, bool FULL, bool EARR, int NT, bool LEAN>
+template <int MODE, bool FULL, bool EARR, int NT, bool LEAN, int LROW = 0>
 __device__ __forceinline__ void scalar_node(const StepArgs &a, Sh &sh, const int s, const int lane, const bool act,
                                             const int x, const int y, LeanAddr &la, double *W, double *mom_sh,
                                             const int z)
@@ -144,12 +144,12 @@ __device__ __forceinline__ void scalar_node(const StepArgs &a, Sh &sh, const int
     const bool is_temp = (s == 3);
     const double Ks = s == 1 ? c.K : c.Kn;
     double S[27];
-    if (LEAN) lean_set_z(la, lin, c, z); else set_z(nb, c, z);
+    if (LEAN) { lean_set_z(la, lin, c, z); if (LROW > 0) lean_set_pim(la); } else set_z(nb, c, z);
     const bool bottom = LEAN ? false : (z == 0);
     const bool wall = LEAN ? false : (bottom || (z == c.NZ - 1));
     double *Wn = W + (size_t)(bottom ? 0 : 27) * c.plane;
     if (LEAN) {
-        gather27_lean<MODE>(la, S);
+        gather27_lean<MODE, LROW>(la, S);
 #ifdef EK_ODD_PREFETCH
         if (MODE == EK_MODE_AA_ODD && z + 1 < c.NZ - 2) prefetch27_lean_odd(la, c.lplane);
 #endif
@@ -185,17 +185,18 @@ __device__ __forceinline__ void scalar_node(const StepArgs &a, Sh &sh, const int
     // rest population: relaxed in place (LBM.cu:1712-1714); wall rule LBM.cu:2131,2231,2385
     const double O0 = S[0] - wp * (S[0] - wcm[0] * omusq);
     if (act) {
-        if (LEAN) lean_ptr(la.b[1], la.oxy[1][1])[0] = O0;
+        if (LEAN && LROW > 0) la.pim[1][1][0] = O0;
+        else if (LEAN) lean_ptr(la.b[1], la.oxy[1][1])[0] = O0;
         else if (!wall) lout[nb.lc()] = O0;
         else if (!is_temp) Wn[0] = O0;
         else if (bottom) Wn[0] = -O0 + c.twoTw[0];
         else Wn[0] = -O0;
     }
-    ScalarPairs<MODE, LEAN, 0>::run(S, wcm, omusq, vtx, vty, vtz, wp, wmn, wall, bottom, is_temp, c, lout, nb, la, z, Wn,
-                                    act);
+    ScalarPairs<MODE, LEAN, 0, LROW>::run(S, wcm, omusq, vtx, vty, vtz, wp, wmn, wall, bottom, is_temp, c, lout, nb, la, z,
+                                          Wn, act);
 }
 
-template <int MODE, bool FULL, bool EARR, int NT, bool LEANOK = false>
+template <int MODE, bool FULL, bool EARR, int NT, bool LEANOK = false, int LROW = 0>
 __device__ __forceinline__ void scalar_role(const StepArgs &a, Sh &sh, const int s, const int lane, const bool act,
                                             const int x, const int y, const int pi, const int z0, const int z1)
 {
@@ -228,7 +229,11 @@ __device__ __forceinline__ void scalar_role(const StepArgs &a, Sh &sh, const int
     }
 
     for (int z = z0; z < z1; ++z) {
-        if (LEANOK && z >= 2 && z < c.NZ - 2) scalar_node<MODE, FULL, false, NT, true>(a, sh, s, lane, act, x, y, la, W, mom_sh, z);
+        if (LEANOK && z >= 2 && z < c.NZ - 2) {
+            // rows y-1..y+1 without periodic wrap: the row stride is an immediate (LROW)
+            if (LROW > 0 && y > 0 && y < c.NY - 1) scalar_node<MODE, FULL, false, NT, true, LROW>(a, sh, s, lane, act, x, y, la, W, mom_sh, z);
+            else scalar_node<MODE, FULL, false, NT, true>(a, sh, s, lane, act, x, y, la, W, mom_sh, z);
+        }
         else scalar_node<MODE, FULL, EARR, NT, false>(a, sh, s, lane, act, x, y, la, W, mom_sh, z);
     }
 }
@@ -259,7 +264,7 @@ __device__ __forceinline__ void fluid_pair_trt(const double S[27], const double 
     Ob = b - (np_ - nm_) + c.dt * (Fp - Fm);
 }
 
-template <int MODE, bool LEAN, int p>
+template <int MODE, bool LEAN, int p, int LROW = 0>
 struct FluidPairs {
     static __device__ __forceinline__ void run(const double S[27], double wcr[4], double omusq, const double u[3],
                                                const double F[3], double uF, bool wall, bool top, const EkConst &c,
@@ -280,14 +285,14 @@ struct FluidPairs {
             }
         }
         if (act) {
-            putx<MODE, d, LEAN>(lout, nb, la, Oa);
-            putx<MODE, o, LEAN>(lout, nb, la, Ob);
+            putx<MODE, d, LEAN, LROW>(lout, nb, la, Oa);
+            putx<MODE, o, LEAN, LROW>(lout, nb, la, Ob);
         }
-        FluidPairs<MODE, LEAN, p + 1>::run(S, wcr, omusq, u, F, uF, wall, top, c, lout, nb, la, act);
+        FluidPairs<MODE, LEAN, p + 1, LROW>::run(S, wcr, omusq, u, F, uF, wall, top, c, lout, nb, la, act);
     }
 };
-template <int MODE, bool LEAN>
-struct FluidPairs<MODE, LEAN, 13> {
+template <int MODE, bool LEAN, int LROW>
+struct FluidPairs<MODE, LEAN, 13, LROW> {
     static __device__ __forceinline__ void run(const double *, double *, double, const double *, const double *, double,
                                                bool, bool, const EkConst &, double *, const Nbr &, const LeanAddr &,
                                                bool) {}
@@ -307,7 +312,7 @@ __device__ __forceinline__ void node_force_and_momentum(const EkConst &c, const 
 }
 
 // one node of the fluid set.  LEAN: deep interior (2 <= z <= NZ-3), see LeanAddr.
-template <int MODE, bool FULL, int NT, bool LEAN>
+template <int MODE, bool FULL, int NT, bool LEAN, int LROW = 0>
 __device__ __forceinline__ void fluid_node(const StepArgs &a, Sh &sh, const int lane, const bool act, const int x,
                                            const int y, LeanAddr &la, const double expr1[3], const int z)
 {
@@ -321,7 +326,8 @@ __device__ __forceinline__ void fluid_node(const StepArgs &a, Sh &sh, const int 
     const bool wall = LEAN ? false : ((z == 0) || top);
     if (LEAN) {
         lean_set_z(la, lin, c, z);
-        gather27_lean<MODE>(la, S);
+        if (LROW > 0) lean_set_pim(la);
+        gather27_lean<MODE, LROW>(la, S);
 #ifdef EK_ODD_PREFETCH
         if (MODE == EK_MODE_AA_ODD && z + 1 < c.NZ - 2) prefetch27_lean_odd(la, c.lplane);
 #endif
@@ -371,14 +377,15 @@ __device__ __forceinline__ void fluid_node(const StepArgs &a, Sh &sh, const int 
     double O0 = S[0];
     if (!wall) O0 = S[0] - c.wp[0] * (S[0] - wcr[0] * omusq) + c.dt * (c.sp * (-c.coe[0] * uF));
     if (act) {
-        if (LEAN) lean_ptr(la.b[1], la.oxy[1][1])[0] = O0;
+        if (LEAN && LROW > 0) la.pim[1][1][0] = O0;
+        else if (LEAN) lean_ptr(la.b[1], la.oxy[1][1])[0] = O0;
         else if (MODE == EK_MODE_PUSH) lout[nb.lc()] = O0;
         else if (!wall) lout[nb.lc()] = O0;
     }
-    FluidPairs<MODE, LEAN, 0>::run(S, wcr, omusq, u, F, uF, wall, top, c, lout, nb, la, act);
+    FluidPairs<MODE, LEAN, 0, LROW>::run(S, wcr, omusq, u, F, uF, wall, top, c, lout, nb, la, act);
 }
 
-template <int MODE, bool FULL, int NT, bool LEANOK = false>
+template <int MODE, bool FULL, int NT, bool LEANOK = false, int LROW = 0>
 __device__ __forceinline__ void fluid_role(const StepArgs &a, Sh &sh, const int lane, const bool act, const int x,
                                            const int y, const int z0, const int z1)
 {
@@ -408,7 +415,10 @@ __device__ __forceinline__ void fluid_role(const StepArgs &a, Sh &sh, const int 
     }
 
     for (int z = z0; z < z1; ++z) {
-        if (LEANOK && z >= 2 && z < c.NZ - 2) fluid_node<MODE, FULL, NT, true>(a, sh, lane, act, x, y, la, expr1, z);
+        if (LEANOK && z >= 2 && z < c.NZ - 2) {
+            if (LROW > 0 && y > 0 && y < c.NY - 1) fluid_node<MODE, FULL, NT, true, LROW>(a, sh, lane, act, x, y, la, expr1, z);
+            else fluid_node<MODE, FULL, NT, true>(a, sh, lane, act, x, y, la, expr1, z);
+        }
         else fluid_node<MODE, FULL, NT, false>(a, sh, lane, act, x, y, la, expr1, z);
     }
 }
@@ -419,7 +429,9 @@ __device__ __forceinline__ void fluid_role(const StepArgs &a, Sh &sh, const int 
 #endif
 // (a variant without the store predicate for NX % 32 == 0 was measured: the odd kernel then spills 128 B
 // and the pass takes 5.01 instead of 4.92 ms at 256^3)
-template <int MODE, bool FULL, bool EARR, bool LEAN>
+// LROW > 0: the row stride of the lattice (NXT * 27 * 32 elements) as a compile-time constant, for the odd A-A
+// step of the deep-interior planes (see LeanAddr::pim)
+template <int MODE, bool FULL, bool EARR, bool LEAN, int LROW = 0>
 __global__ void __launch_bounds__(128, EK_MIN_CTAS) ek_step_kernel(const __grid_constant__ StepArgs a)
 {
     __shared__ Sh sh;
@@ -439,8 +451,8 @@ __global__ void __launch_bounds__(128, EK_MIN_CTAS) ek_step_kernel(const __grid_
     const int z0 = (blockIdx.z + a.zblock0) * a.zchunk;
     const int z1 = min(z0 + a.zchunk, c.NZ);
     const int pi = y * c.PX + x;
-    if (role == 0) fluid_role<MODE, FULL, 128, LEAN>(a, sh, lane, act, x, y, z0, z1);
-    else scalar_role<MODE, FULL, EARR, 128, LEAN>(a, sh, role, lane, act, x, y, pi, z0, z1);
+    if (role == 0) fluid_role<MODE, FULL, 128, LEAN, LROW>(a, sh, lane, act, x, y, z0, z1);
+    else scalar_role<MODE, FULL, EARR, 128, LEAN, LROW>(a, sh, role, lane, act, x, y, pi, z0, z1);
 }
 
 #ifdef EK_XCHECK
@@ -1226,10 +1238,36 @@ __global__ void __launch_bounds__(128, EK_MIN_CTAS) ek_march2_kernel(const __gri
 
 #endif  // EK_XCHECK (marching kernels)
 
+// odd A-A step, lean path, row stride as an immediate: instantiated for the x-tile counts of the named configs
+// (C2 128 -> 4, C3 256 -> 8, 512 -> 16, C4 1024 -> 32; x-slabs carry a ghost tile: 130 -> 5, 258 -> 9, 514 -> 17,
+// 1026 -> 33); any other row length takes the generic lean kernel
+template <bool FULL, int NXT>
+bool launch_odd_imm(const StepArgs &a, dim3 grid, cudaStream_t st)
+{
+    if (a.c.NXT != NXT) return false;
+    ek_step_kernel<EK_MODE_AA_ODD, FULL, false, true, NXT * EK_TILE_ELEMS><<<grid, 128, 0, st>>>(a);
+    return true;
+}
+template <bool FULL>
+bool launch_odd_imm_any(const StepArgs &a, dim3 grid, cudaStream_t st)
+{
+#ifdef EK_NO_ROW_IMMEDIATE
+    return false;
+#else
+    return launch_odd_imm<FULL, 4>(a, grid, st) || launch_odd_imm<FULL, 5>(a, grid, st) ||
+           launch_odd_imm<FULL, 8>(a, grid, st) || launch_odd_imm<FULL, 9>(a, grid, st) ||
+           launch_odd_imm<FULL, 16>(a, grid, st) || launch_odd_imm<FULL, 17>(a, grid, st) ||
+           launch_odd_imm<FULL, 32>(a, grid, st) || launch_odd_imm<FULL, 33>(a, grid, st);
+#endif
+}
+
 template <int MODE>
 cudaError_t launch_mode(const StepArgs &a, bool full, bool earr, bool lean, dim3 grid, cudaStream_t st)
 {
     constexpr bool AA = (MODE != EK_MODE_PUSH);
+    if (MODE == EK_MODE_AA_ODD && lean && !earr && a.row_imm) {
+        if (full ? launch_odd_imm_any<true>(a, grid, st) : launch_odd_imm_any<false>(a, grid, st)) return cudaGetLastError();
+    }
     if (full) {
         if (earr) ek_step_kernel<MODE, true, true, false><<<grid, 128, 0, st>>>(a);
         else if (lean && AA) ek_step_kernel<MODE, true, false, AA><<<grid, 128, 0, st>>>(a);

@@ -164,6 +164,10 @@ __device__ __forceinline__ void efield_at(const StepArgs &a, const Nbr &nb, int 
 struct LeanAddr {
     unsigned oxy[3][3];  // [cy+1][cx+1]: lattice element offset of column (x+cx, y+cy) within a plane
     double *b[3];        // lattice base of the planes z-1, z, z+1
+    // LROW > 0 (row stride known at compile time, rows y-1..y+1 do not wrap): pim[k][i] = plane z-1+k, row y,
+    // column x-1+i, slot 0 -- every access of the node is then "one of nine pointers + an immediate"
+    // ((cy * LROW + slot * 32) * 8 bytes) instead of a 64-bit address formed per access
+    double *pim[3][3];
     int fc, fxm, fxp, fym, fyp;  // field offsets within a plane: centre, x-1, x+1, y-1, y+1
     long long fdq;               // y*dq_sy + x of the c+ - c- array
 };
@@ -193,10 +197,24 @@ __device__ __forceinline__ void lean_set_z(LeanAddr &la, double *lat, const EkCo
     la.b[2] = la.b[1] + c.lplane;
 }
 
-template <int MODE>
+__device__ __forceinline__ void lean_set_pim(LeanAddr &la)
+{
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) la.pim[k][i] = la.b[k] + la.oxy[1][i];
+}
+
+template <int MODE, int LROW = 0>
 __device__ __forceinline__ void gather27_lean(const LeanAddr &la, double S[27])
 {
-    if (MODE == EK_MODE_AA_ODD) {
+    if (MODE == EK_MODE_AA_ODD && LROW > 0) {
+#pragma unroll
+        for (int d = 0; d < 27; ++d) {
+            const double *q = la.pim[1 - ek_cz(d)][1 - ek_cx(d)] + (-ek_cy(d) * LROW + ek_opp(d) * EK_TILE);
+            S[d] = EK_LD(q);
+        }
+    } else if (MODE == EK_MODE_AA_ODD) {
 #pragma unroll
         for (int d = 0; d < 27; ++d) {
             const double *q = lean_ptr(la.b[1 - ek_cz(d)], la.oxy[1 - ek_cy(d)][1 - ek_cx(d)]);
@@ -227,10 +245,13 @@ __device__ __forceinline__ void prefetch27_lean_odd(const LeanAddr &la, unsigned
     }
 }
 
-template <int MODE, int d, bool LEAN>
+template <int MODE, int d, bool LEAN, int LROW = 0>
 __device__ __forceinline__ void putx(double *lat, const Nbr &nb, const LeanAddr &la, double v)
 {
-    if (LEAN) {
+    if (LEAN && MODE == EK_MODE_AA_ODD && LROW > 0) {
+        double *q = la.pim[1 + ek_cz(d)][1 + ek_cx(d)] + (ek_cy(d) * LROW + d * EK_TILE);
+        EK_ST(q, v);
+    } else if (LEAN) {
         if (MODE == EK_MODE_AA_EVEN) {
             double *q = lean_ptr(la.b[1], la.oxy[1][1]);
             EK_ST(q + ek_opp(d) * EK_TILE, v);

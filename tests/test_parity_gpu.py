@@ -571,16 +571,18 @@ def test_reference_signature_shim(ek):
     check(util.field_errors(got, want))
 
 
-@pytest.mark.parametrize("NX", [40, 64, 96])
+@pytest.mark.parametrize("NX", [40, 64, 96, 128, 256])
 def test_kernel_variants_agree(ek, NX):
-    """LBM kernel variants: 0 (default: z-walking CTAs, lean deep-interior path), 5 / 6 (x-marching rows
+    """LBM kernel variants: 0 (default: z-walking CTAs, lean deep-interior path; for NX = 128, 256 (4, 8 x-tiles)
+    the odd step takes the instantiation with the row stride as an immediate), 4 (the generic lean kernel for
+    every row length), 5 / 6 (x-marching rows
     for the odd A-A step when NX % 32 == 0: sector-aligned stores / aligned loads too), 3 (general node path
     everywhere) and the cross-check build's five-warp kernel 2 chain the sums in the reference's
     order and must agree bit for bit; the eight-warp kernel 1 adds two partial sums."""
     over = dict(NX=NX, NY=5, NZ=21, uw=1.0e-4, exf=1.0e6)
     init = synthetic_init(over)
     res = {}
-    for kernel in (0, 1, 2, 3, 5, 6):
+    for kernel in (0, 1, 2, 3, 4, 5, 6):
         for mode in (ek.STREAM_AA, ek.STREAM_PUSH):
             sim = ek.Simulation(ek.default_params(**over), stream_mode=mode, zchunk=6, xcheck=kernel in (1, 2, 5, 6))
             sim.set_option("kernel", kernel)
