@@ -151,7 +151,9 @@ __device__ __forceinline__ void scalar_node(const StepArgs &a, Sh &sh, const int
     if (LEAN) {
         gather27_lean<MODE, LROW>(la, S);
 #ifdef EK_ODD_PREFETCH
-        if (MODE == EK_MODE_AA_ODD && z + 1 < c.NZ - 2) prefetch27_lean_odd(la, c.lplane);
+        if (MODE == EK_MODE_AA_ODD && z + 1 < c.NZ - 2) {
+            if (LROW > 0) prefetch27_lean_odd_imm<LROW>(la, c.lplane); else prefetch27_lean_odd(la, c.lplane);
+        }
 #endif
     } else if (wall) {
 #pragma unroll
@@ -329,7 +331,9 @@ __device__ __forceinline__ void fluid_node(const StepArgs &a, Sh &sh, const int 
         if (LROW > 0) lean_set_pim(la);
         gather27_lean<MODE, LROW>(la, S);
 #ifdef EK_ODD_PREFETCH
-        if (MODE == EK_MODE_AA_ODD && z + 1 < c.NZ - 2) prefetch27_lean_odd(la, c.lplane);
+        if (MODE == EK_MODE_AA_ODD && z + 1 < c.NZ - 2) {
+            if (LROW > 0) prefetch27_lean_odd_imm<LROW>(la, c.lplane); else prefetch27_lean_odd(la, c.lplane);
+        }
 #endif
     } else {
         set_z(nb, c, z);

@@ -161,8 +161,9 @@ ek_status ek_set_poisson_dc(ek_handle *h, int mode, double ghat0);
  * "profile" (1: time every LBM/Poisson launch with CUDA events),
  * "graph" (ek_step replays a CUDA graph of two coupled steps: 1 on, 0 off,
  * -1 automatic = grids below 4 M cells, which are launch-latency bound),
- * "kernel" (0 default: z-walking CTAs with the lean deep-interior node path; 3: general node
- * path everywhere).
+ * "kernel" (0 default: z-walking CTAs with the lean deep-interior node path, the odd A-A step with
+ * the lattice row stride as a compile-time immediate where an instantiation exists; 4: the generic
+ * lean kernel for every row length; 3: general node path everywhere).
  * Cross-check build only (libek_b200_xcheck.so, ek_is_xcheck_build()):
  * "poisson_path" 1 = the reference's odd-extension 3-D FFT (poisson.cu:75-103
  * literally), "kernel" 1/2 = eight-/five-warp LBM kernels, 5/6 = x-marching rows for the odd
