@@ -151,7 +151,7 @@ __device__ __forceinline__ void scalar_node(const StepArgs &a, Sh &sh, const int
     if (LEAN) {
         gather27_lean<MODE, LROW>(la, S);
 #ifdef EK_ODD_PREFETCH
-        if (MODE == EK_MODE_AA_ODD && z + 1 < c.NZ - 2) {
+        if (MODE == EK_MODE_AA_ODD && z + 1 < la.zend) {
             if (LROW > 0) prefetch27_lean_odd_imm<LROW>(la, c.lplane); else prefetch27_lean_odd(la, c.lplane);
         }
 #endif
@@ -211,6 +211,7 @@ __device__ __forceinline__ void scalar_role(const StepArgs &a, Sh &sh, const int
         Nbr nb;
         set_xy(nb, c, x, y);
         lean_init(la, nb);
+        la.zend = z1 < c.NZ - 2 ? z1 : c.NZ - 2;
     }
 
     if (z0 == 0) {
@@ -331,7 +332,7 @@ __device__ __forceinline__ void fluid_node(const StepArgs &a, Sh &sh, const int 
         if (LROW > 0) lean_set_pim(la);
         gather27_lean<MODE, LROW>(la, S);
 #ifdef EK_ODD_PREFETCH
-        if (MODE == EK_MODE_AA_ODD && z + 1 < c.NZ - 2) {
+        if (MODE == EK_MODE_AA_ODD && z + 1 < la.zend) {
             if (LROW > 0) prefetch27_lean_odd_imm<LROW>(la, c.lplane); else prefetch27_lean_odd(la, c.lplane);
         }
 #endif
@@ -401,6 +402,7 @@ __device__ __forceinline__ void fluid_role(const StepArgs &a, Sh &sh, const int 
         set_xy(nb, c, x, y);
         lean_init(la, nb);
         la.fdq = (long long)y * c.dq_sy + x;
+        la.zend = z1 < c.NZ - 2 ? z1 : c.NZ - 2;
     }
 
     if (z0 == 0) {

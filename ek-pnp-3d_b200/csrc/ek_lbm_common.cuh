@@ -168,6 +168,7 @@ struct LeanAddr {
     // column x-1+i, slot 0 -- every access of the node is then "one of nine pointers + an immediate"
     // ((cy * LROW + slot * 32) * 8 bytes) instead of a 64-bit address formed per access
     double *pim[3][3];
+    int zend;            // prefetch of the next z-iteration only inside this CTA's chunk: z + 1 < zend
     int fc, fxm, fxp, fym, fyp;  // field offsets within a plane: centre, x-1, x+1, y-1, y+1
     long long fdq;               // y*dq_sy + x of the c+ - c- array
 };
