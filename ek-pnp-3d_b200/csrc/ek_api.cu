@@ -92,8 +92,9 @@ void ek_compute_consts(const ek_params &p, EkConst &c, bool slab)
     c.voltage = p.voltage; c.voltage2 = p.voltage2;
 }
 
-// z-planes a CTA walks.  Large grids: 16 (measured best at 256^3, 4.94 ms vs 4.95 at 32 and
-// 4.99 at 128).  Small grids need more CTAs than (x-tiles * rows) to fill 148 SMs x 4 CTAs:
+// z-planes a CTA walks.  Large grids: 8 (round 2, with the prefetching odd kernel at 256^3: 5.09 ms per step
+// against 5.13 at 16, 5.20 at 32, 5.31 at 64; no difference on 1024-wide rows; round 1's kernel had its
+// optimum at 16).  Small grids need more CTAs than (x-tiles * rows) to fill 148 SMs x 4 CTAs:
 // 50x8x51 runs its LBM pass in 16 us with 2 planes per CTA against 87 us with 32.  At least 2,
 // so that the owner of the z = 0 node also owns z = 1 (LBM.cu:663-801).
 int ek_auto_zchunk(const EkConst &c)
@@ -101,7 +102,7 @@ int ek_auto_zchunk(const EkConst &c)
     const long long cols = (long long)((c.NX + 31) / 32) * c.NY;
     long long z = cols * c.NZ / (148LL * 4 * 8);
     if (z < 2) z = 2;
-    if (z > 16) z = 16;
+    if (z > 8) z = 8;
     return (int)z;
 }
 
