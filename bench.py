@@ -288,7 +288,13 @@ def bench_ranks(ek, dist, torch, args, w, local_rank):
     mlups = cells * args.steps / (ms * 1e-3) / 1e6
     zchunk_used = int(rs.counter("zchunk"))
     K = rs.chunks()
-    phases = {"pipelined_main_stream": rs.profile(4, False), "sequential_no_overlap": rs.profile(4, True)}
+    def _profile(r_, sequential):
+        r_.sync()
+        dist.barrier()          # the ranks enter together: otherwise the first phase absorbs their skew
+        torch.cuda.synchronize()
+        r_.step(2)              # ... and are in step with each other when the marks start
+        return r_.profile(4, sequential)
+    phases = {"pipelined_main_stream": _profile(rs, False), "sequential_no_overlap": _profile(rs, True)}
     nccl_version = ek.load_library().ek_rank_nccl_version()
 
     # ---- end to end through the C ABI with HOST buffers: every rank uploads its slab of the 11
@@ -334,7 +340,7 @@ def bench_ranks(ek, dist, torch, args, w, local_rank):
                 r4.init()
                 tried[K4] = _timed_ranks(r4, dist, torch, steps4, max(args.warmup, 10))
                 if K4 == 0:
-                    ph4 = {"pipelined_main_stream": r4.profile(4, False), "sequential_no_overlap": r4.profile(4, True)}
+                    ph4 = {"pipelined_main_stream": _profile(r4, False), "sequential_no_overlap": _profile(r4, True)}
                 r4.close()
             K4 = min(tried, key=tried.get)
             ms4 = tried[K4]
