@@ -231,13 +231,18 @@ __device__ __forceinline__ void scalar_role(const StepArgs &a, Sh &sh, const int
         bar_velocity<NT>();
     }
 
-    for (int z = z0; z < z1; ++z) {
-        if (LEANOK && z >= 2 && z < c.NZ - 2) {
-            // rows y-1..y+1 without periodic wrap: the row stride is an immediate (LROW)
-            if (LROW > 0 && y > 0 && y < c.NY - 1) scalar_node<MODE, FULL, false, NT, true, LROW>(a, sh, s, lane, act, x, y, la, W, mom_sh, z);
-            else scalar_node<MODE, FULL, false, NT, true>(a, sh, s, lane, act, x, y, la, W, mom_sh, z);
+    // rows y-1..y+1 without periodic wrap: the row stride is an immediate (LROW).  Two copies of the loop, so
+    // that the register allocation of each is its own (the immediate form needs 3 of the 9 column offsets)
+    if (LROW > 0 && y > 0 && y < c.NY - 1) {
+        for (int z = z0; z < z1; ++z) {
+            if (LEANOK && z >= 2 && z < c.NZ - 2) scalar_node<MODE, FULL, false, NT, true, LROW>(a, sh, s, lane, act, x, y, la, W, mom_sh, z);
+            else scalar_node<MODE, FULL, EARR, NT, false>(a, sh, s, lane, act, x, y, la, W, mom_sh, z);
         }
-        else scalar_node<MODE, FULL, EARR, NT, false>(a, sh, s, lane, act, x, y, la, W, mom_sh, z);
+    } else {
+        for (int z = z0; z < z1; ++z) {
+            if (LEANOK && z >= 2 && z < c.NZ - 2) scalar_node<MODE, FULL, false, NT, true>(a, sh, s, lane, act, x, y, la, W, mom_sh, z);
+            else scalar_node<MODE, FULL, EARR, NT, false>(a, sh, s, lane, act, x, y, la, W, mom_sh, z);
+        }
     }
 }
 
@@ -420,12 +425,16 @@ __device__ __forceinline__ void fluid_role(const StepArgs &a, Sh &sh, const int 
         bar_velocity<NT>();
     }
 
-    for (int z = z0; z < z1; ++z) {
-        if (LEANOK && z >= 2 && z < c.NZ - 2) {
-            if (LROW > 0 && y > 0 && y < c.NY - 1) fluid_node<MODE, FULL, NT, true, LROW>(a, sh, lane, act, x, y, la, expr1, z);
-            else fluid_node<MODE, FULL, NT, true>(a, sh, lane, act, x, y, la, expr1, z);
+    if (LROW > 0 && y > 0 && y < c.NY - 1) {
+        for (int z = z0; z < z1; ++z) {
+            if (LEANOK && z >= 2 && z < c.NZ - 2) fluid_node<MODE, FULL, NT, true, LROW>(a, sh, lane, act, x, y, la, expr1, z);
+            else fluid_node<MODE, FULL, NT, false>(a, sh, lane, act, x, y, la, expr1, z);
         }
-        else fluid_node<MODE, FULL, NT, false>(a, sh, lane, act, x, y, la, expr1, z);
+    } else {
+        for (int z = z0; z < z1; ++z) {
+            if (LEANOK && z >= 2 && z < c.NZ - 2) fluid_node<MODE, FULL, NT, true>(a, sh, lane, act, x, y, la, expr1, z);
+            else fluid_node<MODE, FULL, NT, false>(a, sh, lane, act, x, y, la, expr1, z);
+        }
     }
 }
 
