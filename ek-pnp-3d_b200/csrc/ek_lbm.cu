@@ -212,6 +212,8 @@ __device__ __forceinline__ void scalar_role(const StepArgs &a, Sh &sh, const int
         set_xy(nb, c, x, y);
         lean_init(la, nb);
         la.zend = z1 < c.NZ - 2 ? z1 : c.NZ - 2;
+        la.pf_m = !(x == 0 && c.xlo >= c.NX);       // x-1 / x+1 is a ghost column of an x-slab
+        la.pf_p = !(x == c.NX - 1 && c.xhi >= c.NX);
     }
 
     if (z0 == 0) {
@@ -408,6 +410,8 @@ __device__ __forceinline__ void fluid_role(const StepArgs &a, Sh &sh, const int 
         lean_init(la, nb);
         la.fdq = (long long)y * c.dq_sy + x;
         la.zend = z1 < c.NZ - 2 ? z1 : c.NZ - 2;
+        la.pf_m = !(x == 0 && c.xlo >= c.NX);       // x-1 / x+1 is a ghost column of an x-slab
+        la.pf_p = !(x == c.NX - 1 && c.xhi >= c.NX);
     }
 
     if (z0 == 0) {

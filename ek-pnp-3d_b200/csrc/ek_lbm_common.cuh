@@ -169,6 +169,8 @@ struct LeanAddr {
     // ((cy * LROW + slot * 32) * 8 bytes) instead of a 64-bit address formed per access
     double *pim[3][3];
     int zend;            // prefetch of the next z-iteration only inside this CTA's chunk: z + 1 < zend
+    bool pf_m, pf_p;     // prefetch the x-1 / x+1 column too?  Not when it is a ghost column of a slab: nobody else
+                         // needs the rest of a ghost tile's line
     int fc, fxm, fxp, fym, fyp;  // field offsets within a plane: centre, x-1, x+1, y-1, y+1
     long long fdq;               // y*dq_sy + x of the c+ - c- array
 };
@@ -247,6 +249,8 @@ __device__ __forceinline__ void prefetch27_lean_odd(const LeanAddr &la, unsigned
         const int k = 1 - ek_cz(d);
         double *base = k == 2 ? la.b[2] + lplane : la.b[k + 1];
         const double *q = lean_ptr(base, la.oxy[1 - ek_cy(d)][1 - ek_cx(d)]) + ek_opp(d) * EK_TILE;
+        if (ek_cx(d) > 0 && !la.pf_m) continue;
+        if (ek_cx(d) < 0 && !la.pf_p) continue;
         asm volatile(EK_PF_INSTR " [%0];" ::"l"(q));
     }
 }
@@ -261,6 +265,8 @@ __device__ __forceinline__ void prefetch27_lean_odd_imm(const LeanAddr &la, unsi
     for (int d = 0; d < 27; ++d) {
         const int k = 1 - ek_cz(d), i = 1 - ek_cx(d);
         const double *q = (k == 2 ? p3[i] : la.pim[k + 1][i]) + (-ek_cy(d) * LROW + ek_opp(d) * EK_TILE);
+        if (i == 0 && !la.pf_m) continue;
+        if (i == 2 && !la.pf_p) continue;
         asm volatile(EK_PF_INSTR " [%0];" ::"l"(q));
     }
 }
