@@ -161,6 +161,8 @@ def load_library(path: str | None = None):
     L.ek_multi_set_fields.argtypes = [H, C.POINTER(C.c_void_p)]
     L.ek_multi_slab.argtypes = [H, C.c_int]
     L.ek_multi_slab.restype = C.c_void_p
+    L.ek_multi_wall_current.argtypes = [H, C.POINTER(C.c_double)]
+    L.ek_multi_max_uz.argtypes = [H, C.POINTER(C.c_double)]
     L.ek_multi_last_error.argtypes = [H]
     L.ek_multi_last_error.restype = C.c_char_p
     # one process per GPU, NCCL driven from C++ (ek_rank.cu)
@@ -487,6 +489,16 @@ class MultiSimulation:
 
     def fields(self) -> dict:
         return {n: self.field(n) for n in FIELDS}
+
+    def current(self) -> float:
+        v = C.c_double()
+        self._ck(self.L.ek_multi_wall_current(self.h, C.byref(v)), "ek_multi_wall_current")
+        return v.value
+
+    def max_uz(self) -> float:
+        v = C.c_double()
+        self._ck(self.L.ek_multi_max_uz(self.h, C.byref(v)), "ek_multi_max_uz")
+        return v.value
 
     def checkpoint_save(self, path: str, time: float = 0.0):
         self._ck(self.L.ek_multi_checkpoint_save(self.h, path.encode(), float(time)), "ek_multi_checkpoint_save")

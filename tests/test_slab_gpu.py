@@ -227,3 +227,28 @@ def test_checkpoints_are_interchangeable_between_single_and_multi_gpu_runs(ek, t
     back = sim.fields()
     sim.close()
     check(util.field_errors(back, want))
+
+
+def test_multi_diagnostics_and_step_counter(ek):
+    """ek_multi_wall_current / ek_multi_max_uz against the single-domain diagnostics, with the slabs on
+    DISTINCT devices when the box has them (the per-slab reductions select their own device), and the
+    step counter that ek_multi_checkpoint_save writes"""
+    import torch
+    over = dict(NX=64, NY=6, NZ=13, exf=1.0e6, voltage2=-3.0e-3)
+    init = synthetic_init(over)
+    sim = ek.Simulation(ek.default_params(**over))
+    sim.set_fields(init)
+    sim.init_equilibrium()
+    sim.step(5)
+    want_i, want_u = sim.current(), sim.max_uz()
+    sim.close()
+    ndev = torch.cuda.device_count()
+    m = ek.MultiSimulation(ek.default_params(**over), [0, 1 % ndev])
+    m.set_fields(init)
+    m.init_equilibrium()
+    m.step(5)
+    assert abs(m.current() - want_i) <= 1e-10 * abs(want_i)
+    assert abs(m.max_uz() - want_u) <= 1e-12 * abs(want_u) + 16 * 5.7e-15
+    v = ek.C.c_double()
+    assert m.L.ek_get_counter(ek.C.c_void_p(m.L.ek_multi_slab(m.h, 1)), b"steps", ek.C.byref(v)) == 0 and v.value == 5
+    m.close()
