@@ -255,6 +255,14 @@ __device__ __forceinline__ void prefetch27_lean_odd(const LeanAddr &la, unsigned
     }
 }
 
+// even A-A step: the node's own 27 slots of the next plane (one pointer + immediates)
+__device__ __forceinline__ void prefetch27_lean_even(const LeanAddr &la, unsigned lplane)
+{
+    const double *q = lean_ptr(la.b[2], la.oxy[1][1]);
+#pragma unroll
+    for (int d = 0; d < 27; ++d) asm volatile(EK_PF_INSTR " [%0];" ::"l"(q + d * EK_TILE));
+}
+
 // the same with the row stride as an immediate: the next iteration's planes z, z+1 are pim[1], pim[2] (pointers
 // already formed); plane z+2 costs three 64-bit additions
 template <int LROW>
