@@ -114,8 +114,12 @@ def test_reference_main_links_against_the_shim(tmp_path):
     _, zones = _zones(b / "data.dat")
     assert zones.shape[0] == 4                     # t = 0, i = 1, i = 101, end (main.cu:179,206,253)
     assert np.abs(zones[-1][:, 3]).max() > 0       # the flow has started: ux is not identically zero
-    with open(os.path.join(util.ROOT, "gpurun_out", "dropin_r02.json"), "w") as f:
-        json.dump({"g4_linked_vs_reference_main_data_dat_rel": rep}, f, indent=1)
+    try:        # measured differences for DESIGN.md (scratch directory of the GPU runs; optional)
+        os.makedirs(os.path.join(util.ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(util.ROOT, "gpurun_out", "dropin_r02.json"), "w") as f:
+            json.dump({"g4_linked_vs_reference_main_data_dat_rel": rep}, f, indent=1)
+    except OSError:
+        pass
 
 
 @pytest.mark.skipif(not _have("ek_ref_stock", "ek_main_linked_c1"), reason="oracle/_ref main builds missing")
