@@ -87,6 +87,22 @@ def x_backward(X: torch.Tensor, P: int) -> torch.Tensor:
     return X.view(M, kyl, P, NX // P).permute(2, 0, 1, 3).contiguous()
 
 
+def x_backward_ghost(X: torch.Tensor, P: int) -> torch.Tensor:
+    """x_backward with the two ghost columns of phi inside the transpose (what ek_rank.cu does,
+    ek_slab_poisson_scatter_xg): rank i's block carries its NXl columns plus column (i+1)*NXl and column
+    i*NXl - 1 (periodic in x) -> (P, M, kyl, NXl + 2).  After y_backward the last two columns are the
+    right / left ghost column of phi: no separate phi halo exchange."""
+    M, kyl, NX = X.shape
+    NXl = NX // P
+    X = torch.fft.ifft(X, dim=2, norm="forward")
+    out = torch.empty((P, M, kyl, NXl + 2), dtype=X.dtype, device=X.device)
+    for i in range(P):
+        out[i, :, :, :NXl] = X[:, :, i * NXl:(i + 1) * NXl]
+        out[i, :, :, NXl] = X[:, :, ((i + 1) * NXl) % NX]
+        out[i, :, :, NXl + 1] = X[:, :, (i * NXl - 1) % NX]
+    return out
+
+
 def y_backward(recv: torch.Tensor, NY: int) -> torch.Tensor:
     """recv (P, M, kyl, NXl): every ky chunk of my x block -> (M, NY, NXl) real (unnormalised)"""
     P, M, kyl, NXl = recv.shape

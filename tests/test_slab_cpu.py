@@ -52,8 +52,9 @@ def zsolve_dense(X, p, ky0, NXg, NY):
     return out
 
 
-def run_distributed_poisson(slab, comm, p, dq_local, ranks):
-    """dq_local: {rank: (NZ, NY, NXl)} -> {rank: phi interior (M, NY, NXl)}"""
+def run_distributed_poisson(slab, comm, p, dq_local, ranks, ghosts=False):
+    """dq_local: {rank: (NZ, NY, NXl)} -> {rank: phi interior (M, NY, NXl)}; ghosts: (M, NY, NXl + 2), the last
+    two columns being the right / left ghost column of phi (they travel inside the second transpose)"""
     P = comm.nranks
     nyh, kyl = slab.ky_chunks(p.NY, P)
     send = [slab.y_forward(torch.from_numpy(dq_local[r][1:-1].copy()), P, kyl) for r in ranks]
@@ -62,7 +63,7 @@ def run_distributed_poisson(slab, comm, p, dq_local, ranks):
     for r, rc in zip(ranks, recv):
         X = slab.x_forward(rc)
         X = torch.from_numpy(zsolve_dense(X.numpy(), p, r * kyl, p.NX, p.NY))
-        back.append(slab.x_backward(X, P))
+        back.append(slab.x_backward_ghost(X, P) if ghosts else slab.x_backward(X, P))
     recv = comm.all_to_all(back)
     return {r: slab.y_backward(rc, p.NY).numpy() for r, rc in zip(ranks, recv)}
 
@@ -104,6 +105,24 @@ def test_local_transport_matches_the_oracle(P):
     assert np.abs(full - phi[1:-1]).max() <= 1e-12 * np.abs(phi).max()
 
 
+@pytest.mark.parametrize("P", [1, 2, 3])
+def test_ghost_columns_travel_inside_the_second_transpose(P):
+    """the way back of the native rank driver: rows two columns wider, the ghost columns of phi come out of
+    the inverse y-transform -- they must be the neighbours' edge columns (periodic in x)"""
+    slab = slab_mod()
+    p, dq, phi = oracle_case()
+    parts = slab.partition(p.NX, P)
+    comm = slab.LocalComm(P)
+    got = run_distributed_poisson(slab, comm, p, {r: dq[:, :, a:b] for r, (a, b) in enumerate(parts)}, list(range(P)),
+                                  ghosts=True)
+    scale = np.abs(phi).max()
+    for r, (a, b) in enumerate(parts):
+        assert got[r].shape[2] == (b - a) + 2
+        assert np.abs(got[r][:, :, :b - a] - phi[1:-1, :, a:b]).max() <= 1e-12 * scale
+        assert np.abs(got[r][:, :, b - a] - phi[1:-1, :, b % p.NX]).max() <= 1e-12 * scale          # right ghost
+        assert np.abs(got[r][:, :, b - a + 1] - phi[1:-1, :, (a - 1) % p.NX]).max() <= 1e-12 * scale  # left ghost
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -120,6 +139,9 @@ def _worker(rank, world, port, q):
         a, b = slab.partition(p.NX, world)[rank]
         got = run_distributed_poisson(slab, comm, p, {rank: dq[:, :, a:b]}, [rank])[rank]
         err = float(np.abs(got - phi[1:-1, :, a:b]).max() / np.abs(phi).max())
+        gg = run_distributed_poisson(slab, comm, p, {rank: dq[:, :, a:b]}, [rank], ghosts=True)[rank]
+        err = max(err, float(np.abs(gg[:, :, b - a] - phi[1:-1, :, b % p.NX]).max() / np.abs(phi).max()),
+                  float(np.abs(gg[:, :, b - a + 1] - phi[1:-1, :, (a - 1) % p.NX]).max() / np.abs(phi).max()))
         m = comm.max_over_ranks(float(rank))
         # all-to-all into preallocated chunk buffers (what the native Poisson stage hands to the transport):
         # part i of my send buffer must arrive as part `rank` of rank i's receive buffer
