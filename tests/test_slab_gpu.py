@@ -252,3 +252,27 @@ def test_multi_diagnostics_and_step_counter(ek):
     v = ek.C.c_double()
     assert m.L.ek_get_counter(ek.C.c_void_p(m.L.ek_multi_slab(m.h, 1)), b"steps", ek.C.byref(v)) == 0 and v.value == 5
     m.close()
+
+
+def test_c4_shaped_slabs_match_the_single_domain_run(ek):
+    """config C4's decomposition on one device: NX = 1024 split into 8 x-slabs of 128 columns (four x-tiles +
+    the ghost tile, the row-stride-immediate kernel instantiation for slabs), small NY / NZ, pressure- and
+    electro-driven, 3-D perturbed start; all 11 fields against the single-domain run"""
+    over = dict(NX=1024, NY=8, NZ=37, exf=2.0e6, chargeinf=0.002)
+    init = synthetic_init(over)
+    want, _ = product_run(ek, over, init, 6, ek.STREAM_AA)
+    m = ek.MultiSimulation(ek.default_params(**over), [0] * 8)
+    m.set_fields(init)
+    m.init_equilibrium()
+    m.step(4)
+    m.step(2)
+    got = m.fields()
+    m.close()
+    check(util.field_errors(got, want))
+    # and through the per-rank driver's pipeline pieces on one rank (ghost columns inside the transpose)
+    rs = ek.RankSimulation(ek.default_params(**over), 0, 0, 1, None)
+    rs.set_fields(init)
+    rs.init_equilibrium()
+    rs.step(6)
+    check(util.field_errors(rs.fields(), want))
+    rs.close()
