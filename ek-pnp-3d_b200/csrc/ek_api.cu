@@ -651,6 +651,9 @@ ek_status ek_step(ek_handle *h, int nsteps)
 //     downloaded behind it; phi and E follow after the last solve.
 // Same results as the plain sequence, bit for bit (tests).  Host buffers should be pinned.
 // ---------------------------------------------------------------------------
+static ek_status run_from_host_pipelined(ek_handle *h, const double *const in[EK_NFIELDS], int nsteps,
+                                         double *const out[EK_NFIELDS], int nblocks);
+
 ek_status ek_run_from_host(ek_handle *h, const double *const in[EK_NFIELDS], int nsteps, double *const out[EK_NFIELDS])
 {
     if (!h || !in || !out || nsteps < 1) return EK_ERR_INVALID;
@@ -672,6 +675,22 @@ ek_status ek_run_from_host(ek_handle *h, const double *const in[EK_NFIELDS], int
         for (int k = 0; k < EK_NFIELDS && st == EK_OK; ++k) st = ek_get_field(h, k, out[k], 0);
         return st;
     }
+    st = run_from_host_pipelined(h, in, nsteps, out, nblocks);
+    if (st != EK_OK) {
+        // a job that stopped half way leaves nothing to continue from: drain both streams, back to "not initialised"
+        if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+        cudaStreamSynchronize(h->stream);
+        h->fields_ready = false;
+        h->pops_ready = false;
+    }
+    return st;
+}
+
+static ek_status run_from_host_pipelined(ek_handle *h, const double *const in[EK_NFIELDS], int nsteps,
+                                         double *const out[EK_NFIELDS], int nblocks)
+{
+    const EkConst &c = h->c;
+    ek_status st = EK_OK;
     if (!h->copy_stream) EK_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     const int G = nblocks < 8 ? nblocks : 8;      // plane groups (multiples of the LBM kernel's z-blocks)
     while ((int)h->job_events.size() < 2 * G + 2) {

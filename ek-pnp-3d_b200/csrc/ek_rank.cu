@@ -334,6 +334,7 @@ void release(ek_rank *r)
         for (cudaEvent_t e : *v) cudaEventDestroy(e);
     for (cudaEvent_t e : {r->ev_side, r->ev_main, r->ev_halo, r->ev_back, r->ev_bnd})
         if (e) cudaEventDestroy(e);
+    for (auto &m : r->marks) cudaEventDestroy(m.second);
     for (double *p : {r->to_l, r->to_r, r->from_l, r->from_r, r->pto_l, r->pto_r, r->pfrom_l, r->pfrom_r}) cudaFree(p);
     if (r->h) ek_destroy(r->h);
     delete r;
@@ -572,8 +573,12 @@ ek_status ek_rank_profile(ek_rank *r, int nsteps, int sequential, char *json, in
     ek_status st = ek_rank_step(r, nsteps);
     r->profile = false;
     r->overlap = ov; r->overlap_back = ovb;
-    if (st != EK_OK) return st;
-    RK(r, ek_rank_sync(r));
+    auto drop_marks = [&]() {
+        for (auto &m : r->marks) cudaEventDestroy(m.second);
+        r->marks.clear();
+    };
+    if (st == EK_OK) st = ek_rank_sync(r);
+    if (st != EK_OK) { drop_marks(); return st; }
     std::vector<std::pair<std::string, double>> acc;
     for (size_t i = 1; i < r->marks.size(); ++i) {
         if (!strcmp(r->marks[i].first, "begin")) continue;
@@ -584,8 +589,7 @@ ek_status ek_rank_profile(ek_rank *r, int nsteps, int sequential, char *json, in
             if (a.first == r->marks[i].first) { a.second += ms; found = true; }
         if (!found) acc.emplace_back(r->marks[i].first, ms);
     }
-    for (auto &m : r->marks) cudaEventDestroy(m.second);
-    r->marks.clear();
+    drop_marks();
     std::string out = "{";
     for (size_t i = 0; i < acc.size(); ++i) {
         char buf[160];
