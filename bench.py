@@ -184,7 +184,7 @@ def run_reference(args, rank: int):
         line = {"impl": "reference", "metric": "coupled_step_mlups", "value": cb["value"], "unit": "MLUPS",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic", "config": {"workload": w["name"], "note": "reference binary missing: " + "; ".join(tried)},
+                "data": "synthetic", "config": {"workload": w["name"], "note": "the reference's CUDA build did not run here (no binary or no GPU), CPU restatement timed instead: " + "; ".join(tried)},
                 "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)

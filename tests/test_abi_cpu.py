@@ -96,3 +96,24 @@ def test_shim_exports_the_reference_signatures():
         assert any(l.strip().endswith(" " + g) and " w " in l for l in out.splitlines()), g
     for f in ("ek_shim_configure", "ek_shim_bind_potential", "ek_shim_handle"):
         assert f" T {f}" in out, f
+
+
+def test_reference_arm_prints_a_contract_line_without_a_gpu():
+    """`bench.py --impl reference` on a box where the reference's CUDA build cannot run (this container: no GPU)
+    falls back to timing the CPU restatement and still prints ONE JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU box: the reference's own build runs (covered by the driver's reference arm)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "3"],
+                         check=True, capture_output=True, text=True, timeout=600).stdout
+    lines = [l for l in out.splitlines() if l.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["metric"] == "coupled_step_mlups" and line["unit"] == "MLUPS"
+    assert line["higher_is_better"] is True and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
