@@ -138,6 +138,53 @@ void ek_slab_poisson_destroy(ek_handle *h)
 
 extern "C" {
 
+// Chunks of the pipelined stage in LBM z-blocks: fills bounds[0..K] (bounds[0] = 0, bounds[K] = nblocks, strictly
+// increasing) and returns K <= EK_MAX_CHUNKS.  nchunks >= 1: that many equal chunks (at most one per z-block).
+// nchunks <= 0: automatic -- seven chunks of sizes 1:2:3:4:3:2:1 from 16 z-blocks on (measured best at 2 x 134 M
+// cells, 46.0 ms per step against 46.4 for four equal chunks: the LAST chunk's forward half and the FIRST chunks'
+// way back are the parts of the stage that nothing overlaps, so they are the small ones), up to four equal chunks
+// below.  sizes_csv (the EK_POISSON_CHUNK_BLOCKS environment variable, e.g. "2,3,4,4,2,1") overrides both when its
+// entries are positive and add up to nblocks.  Pure host arithmetic (CPU-tested).
+int ek_slab_poisson_plan_chunks(int nblocks, int nchunks, const char *sizes_csv, int *bounds)
+{
+    if (nblocks < 1 || !bounds) return 0;
+    int K = nchunks < 1 ? 1 : (nchunks > nblocks ? nblocks : nchunks);
+    if (K > EK_MAX_CHUNKS) K = EK_MAX_CHUNKS;
+    if (nchunks <= 0 && nblocks >= 16) {
+        static const int w[7] = {1, 2, 3, 4, 3, 2, 1};
+        K = 7;
+        bounds[0] = 0;
+        int acc = 0;
+        for (int k = 0; k < 7; ++k) {
+            acc += w[k];
+            bounds[k + 1] = (int)((long long)nblocks * acc / 16);
+            if (bounds[k + 1] <= bounds[k]) bounds[k + 1] = bounds[k] + 1;
+        }
+        bounds[7] = nblocks;
+    } else {
+        if (nchunks <= 0) K = nblocks < 4 ? nblocks : 4;
+        for (int k = 0; k <= K; ++k) bounds[k] = (int)((long long)nblocks * k / K);
+    }
+    if (sizes_csv) {
+        int sizes[EK_MAX_CHUNKS], n = 0, sum = 0;
+        bool ok = true;
+        for (const char *q = sizes_csv; *q;) {
+            if (n == EK_MAX_CHUNKS) { ok = false; break; }
+            sizes[n] = atoi(q);
+            if (sizes[n] < 1) { ok = false; break; }
+            sum += sizes[n++];
+            while (*q && *q != ',') ++q;
+            if (*q == ',') ++q;
+        }
+        if (ok && n >= 1 && sum == nblocks) {
+            K = n;
+            bounds[0] = 0;
+            for (int k = 0; k < n; ++k) bounds[k + 1] = bounds[k] + sizes[k];
+        }
+    }
+    return K;
+}
+
 // nchunks groups of the LBM z-blocks ("zchunk" planes each) define the chunks.
 ek_status ek_slab_poisson_setup(ek_handle *h, int nchunks)
 {
@@ -154,45 +201,8 @@ ek_status ek_slab_poisson_setup(ek_handle *h, int nchunks)
     S.NXl = c.NX; S.NXg = h->NXg; S.NY = c.NY; S.NYH = c.NY / 2 + 1; S.M = c.NZ - 2;
     S.kyl = (S.NYH + S.P - 1) / S.P;
     const int nblocks = (c.NZ + h->zchunk - 1) / h->zchunk;
-    S.K = nchunks < 1 ? 1 : (nchunks > nblocks ? nblocks : nchunks);   // nchunks <= 0: automatic, below
-    if (S.K > EK_MAX_CHUNKS) S.K = EK_MAX_CHUNKS;
-    // chunk sizes in LBM z-blocks.  Default: equal.  EK_POISSON_CHUNK_BLOCKS="2,3,4,4,2,1" sets them explicitly
-    // (their sum must be the number of z-blocks): the LAST chunk's forward half and the FIRST chunks' way back
-    // are the parts of the stage that nothing overlaps, so unequal sizes trade launches for exposed time.
     int bounds[EK_MAX_CHUNKS + 1];
-    if (nchunks <= 0 && nblocks >= 16) {
-        // automatic: seven chunks with sizes 1:2:3:4:3:2:1 -- measured best at 2 x 134 M cells (46.0 ms per step
-        // against 46.4 for four equal chunks): a small last chunk (its forward half is waited for) and small
-        // first chunks (the next step's first LBM launches wait for their way back)
-        static const int w[7] = {1, 2, 3, 4, 3, 2, 1};
-        S.K = 7;
-        bounds[0] = 0;
-        int acc = 0;
-        for (int k = 0; k < 7; ++k) {
-            acc += w[k];
-            bounds[k + 1] = (int)((long long)nblocks * acc / 16);
-            if (bounds[k + 1] <= bounds[k]) bounds[k + 1] = bounds[k] + 1;
-        }
-        bounds[7] = nblocks;
-    } else {
-        if (nchunks <= 0) S.K = nblocks < 4 ? nblocks : 4;
-        for (int k = 0; k <= S.K; ++k) bounds[k] = (int)((long long)nblocks * k / S.K);
-    }
-    if (const char *env = getenv("EK_POISSON_CHUNK_BLOCKS")) {
-        int sizes[EK_MAX_CHUNKS], n = 0, sum = 0;
-        for (const char *q = env; *q && n < EK_MAX_CHUNKS;) {
-            sizes[n] = atoi(q);
-            if (sizes[n] < 1) { n = 0; break; }
-            sum += sizes[n++];
-            while (*q && *q != ',') ++q;
-            if (*q == ',') ++q;
-        }
-        if (n >= 1 && sum == nblocks) {
-            S.K = n;
-            bounds[0] = 0;
-            for (int k = 0; k < n; ++k) bounds[k + 1] = bounds[k] + sizes[k];
-        }
-    }
+    S.K = ek_slab_poisson_plan_chunks(nblocks, nchunks, getenv("EK_POISSON_CHUNK_BLOCKS"), bounds);
     for (int k = 0; k <= S.K; ++k) {
         const int b = bounds[k];     // first LBM z-block of chunk k
         int z = b * h->zchunk;                                   // first plane

@@ -251,6 +251,10 @@ ek_status ek_compute_efield(ek_handle *h);
  * equal parts (part i travels to / comes from rank i). */
 ek_status ek_slab_poisson_setup(ek_handle *h, int nchunks);   /* nchunks <= 0: automatic (7 chunks 1:2:3:4:3:2:1 of the z-blocks, or 4 equal ones) */
 int ek_slab_poisson_chunks(ek_handle *h);
+/* The chunk plan ek_slab_poisson_setup uses, as pure host arithmetic: bounds[0..K] in LBM z-blocks (bounds needs 17
+ * entries), returns K.  sizes_csv: explicit chunk sizes "2,3,4,4,2,1" (what the EK_POISSON_CHUNK_BLOCKS environment
+ * variable holds) or NULL. */
+int ek_slab_poisson_plan_chunks(int nblocks, int nchunks, const char *sizes_csv, int *bounds);
 ek_status ek_slab_poisson_chunk(ek_handle *h, int k, int *block0, int *block1, void **send, void **recv,
                                 long long *count);
 ek_status ek_slab_poisson_forward(ek_handle *h, int k);

@@ -171,3 +171,43 @@ def test_gloo_world_size_2():
         assert ok, f"rank {rank}: neighbour exchange delivered the wrong buffers"
         assert err <= 1e-12, (rank, err)
         assert m == 1.0
+
+
+def plan_chunks(nblocks, nchunks, sizes=None):
+    import ctypes as C
+    lib = util.ek_module().load_library()
+    fn = lib.ek_slab_poisson_plan_chunks
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_int)]
+    bounds = (C.c_int * 17)()
+    K = fn(nblocks, nchunks, None if sizes is None else sizes.encode(), bounds)
+    return K, list(bounds[:K + 1])
+
+
+def test_chunk_plan_of_the_pipelined_poisson_stage():
+    """ek_slab_poisson_plan_chunks (host arithmetic of csrc/ek_slab_poisson.cu): every plan covers the z-blocks
+    exactly once with non-empty chunks; the automatic plan is the measured 1:2:3:4:3:2:1 one on large grids."""
+    # C5 per rank: 256 planes in z-blocks of 8 -> 32 blocks, automatic
+    K, b = plan_chunks(32, 0)
+    assert K == 7 and b == [0, 2, 6, 12, 20, 26, 30, 32]
+    assert [b[i + 1] - b[i] for i in range(K)] == [2, 4, 6, 8, 6, 4, 2]
+    # below 16 z-blocks: up to four equal chunks; tiny grids: one chunk per block
+    assert plan_chunks(15, 0) == (4, [0, 3, 7, 11, 15])
+    assert plan_chunks(3, 0) == (3, [0, 1, 2, 3])
+    assert plan_chunks(1, 0) == (1, [0, 1])
+    # explicit counts: equal chunks, never more than z-blocks or the compiled-in maximum
+    assert plan_chunks(32, 4) == (4, [0, 8, 16, 24, 32])
+    assert plan_chunks(5, 8) == (5, [0, 1, 2, 3, 4, 5])
+    assert plan_chunks(64, 40)[0] == 16
+    # explicit sizes win when they are valid, and are ignored otherwise
+    assert plan_chunks(16, 0, "2,3,4,4,2,1") == (6, [0, 2, 5, 9, 13, 15, 16])
+    assert plan_chunks(16, 2, "2,3,4,4,2") == (2, [0, 8, 16])          # sum != nblocks
+    assert plan_chunks(16, 2, "8,0,8") == (2, [0, 8, 16])              # empty chunk
+    assert plan_chunks(17, 2, ",".join(["1"] * 17)) == (2, [0, 8, 17])  # more chunks than the maximum
+    # every automatic / counted plan: strictly increasing, complete
+    for nblocks in range(1, 200):
+        for nchunks in (0, 1, 2, 3, 4, 7, 16, 50):
+            K, b = plan_chunks(nblocks, nchunks)
+            assert 1 <= K <= 16 and b[0] == 0 and b[-1] == nblocks
+            assert all(b[i + 1] > b[i] for i in range(K)), (nblocks, nchunks, b)
+    assert plan_chunks(0, 0)[0] == 0
